@@ -1,0 +1,165 @@
+/* neon_lbm.h — C ABI of the B200-native (sm_100a) Neon LBM hot path.
+ *
+ * This is the drop-in boundary.  In the reference the path is
+ * entered through
+ *     Neon::set::Container::run(int streamIdx, Neon::DataView)
+ *         libNeonSet/include/Neon/set/Containter.h:25-27
+ *     -> DeviceContainer<Grid,Lambda>::run      container/DeviceContainer.h:88-111
+ *     -> DevSet::launchLambdaOnSpan             libNeonSet/include/Neon/set/DevSet.h:226-261,356-399
+ *     -> GpuDevice::kernel.cudaLaunchKernel     libNeonSys/include/Neon/sys/devices/gpu/GpuDevice.h:151-191
+ * with the LBM lambda of benchmarks/lbm-lid-driven-cavity-flow/src/LbmTools.h:285-325
+ * as payload, and the halo side through dField::newHaloUpdate
+ * (libNeonDomain/include/Neon/domain/details/dGrid/dField.h:84-87).  Every entry
+ * point below names the reference interface it replaces.
+ *
+ * Conventions (all entry points):
+ *  - plain C, no C++/torch types; device buffers are BORROWED from the caller's
+ *    Field (the reference's Field owns its MemSet, dField.h:150-195); nothing is
+ *    allocated or freed inside step calls;
+ *  - asynchronous: work is enqueued on `stream` (a cudaStream_t passed as void*)
+ *    of the CURRENT device and the call returns; completion is observed through
+ *    the caller's stream/event API (Backend::sync, Backend.h:230-261);
+ *  - thread-safe, no global mutable state except the per-thread last-error
+ *    string (one host thread per GPU, DevSet.h:372-391);
+ *  - returns 0 on success, a non-zero nlbm_status otherwise and never throws;
+ *    the C++ veneer converts non-zero into NeonException (GpuDevice.h:165-188).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with NLBM_ERR_CUDA.
+ */
+#ifndef NEON_LBM_H
+#define NEON_LBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLBM_ABI_VERSION 1
+
+typedef enum nlbm_status {
+    NLBM_OK = 0,
+    NLBM_ERR_INVALID = 1,  /* bad descriptor / argument                            */
+    NLBM_ERR_CUDA = 2,     /* a CUDA runtime call failed (see nlbm_last_error)     */
+    NLBM_ERR_GEOMETRY = 3, /* a bulk cell has a neighbour outside the domain       */
+    NLBM_ERR_UNSUPPORTED = 4
+} nlbm_status;
+
+/* Neon::DataView, libNeonCore/include/Neon/core/types/DataView.h:7-12.
+ * INTERNAL = local z in [r, nz_local-r), BOUNDARY = [0,r) U [nz_local-r, nz_local)
+ * (r = z_halo; the reference's BOUNDARY span folds wrongly). */
+typedef enum nlbm_data_view { NLBM_VIEW_STANDARD = 0, NLBM_VIEW_INTERNAL = 1, NLBM_VIEW_BOUNDARY = 2 } nlbm_data_view;
+
+/* Cell classes — values of CellType::Classification,
+ * benchmarks/lbm-lid-driven-cavity-flow/src/CellType.h:5-11.                    */
+typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_BULK = 2, NLBM_UNDEFINED = 3 } nlbm_cell_class;
+
+/* Per-cell flag word (replaces the 8-byte CellType struct, CellType.h:33-34):
+ *   bits  0..26  wallNghBitflag (bit k set <=> cell at x - c_k is not bulk)
+ *   bits 28..29  classification                                                  */
+#define NLBM_FLAG_MASK_BITS 0x07FFFFFFu
+#define NLBM_FLAG_CLASS_SHIFT 28
+#define NLBM_FLAG_CLASS(f) (((f) >> NLBM_FLAG_CLASS_SHIFT) & 3u)
+
+/* Arithmetic mode (bits 0..3 of `opts`).
+ * REFERENCE reproduces the rounding of the reference expressions bit for bit
+ * (double literals promote fp32 expressions to double, LbmTools.h:216-254; no FMA
+ * contraction; IEEE division).  FAST uses fused multiply-add in the storage
+ * precision; results then agree with the reference within the north-star
+ * tolerance (1e-5 relative fp32, 1e-12 fp64), not bitwise.                       */
+#define NLBM_ARITH_REFERENCE 0
+#define NLBM_ARITH_FAST 1
+/* Tuning (bits 4..7: cells per thread along x, 0 = library default; bits 8..11:
+ * log2 of rows per block, 0 = default).  Never changes results.                  */
+#define NLBM_OPT_VEC(v) (((v)&0xF) << 4)
+#define NLBM_OPT_ROWS_LOG2(r) (((r)&0xF) << 8)
+
+/* Dense (dGrid) partition descriptor: one z-slab of the global box on one GPU.
+ * Replaces what the reference kernel receives by value: dSpan {dataView, zHalo,
+ * zBoundary, dim} (dSpan.h:45-48) and dPartition members (dPartition.h:423-434).
+ *
+ * Memory layout (structure of arrays, one plane set per population):
+ *   pop[q][zm][y][x] at  q*pitch_q + zm*pitch_z + y*pitch_y + x      (elements)
+ *   zm = z_local + z_halo in [0, nz_local + 2*z_halo)   ghost planes at both ends
+ *   pitch_y*sizeof(T) is a multiple of 128 bytes; base pointers 128-byte aligned.
+ * The flag array uses the same (zm,y,x) indexing with pitch_y / pitch_z.
+ * (Reference: unpadded SoA, dField_imp.h:67-87.)                                 */
+typedef struct nlbm_dense_desc {
+    void*     pop_in;   /* device, borrowed: populations read  (fIn,  const STENCIL)  */
+    void*     pop_out;  /* device, borrowed: populations written (fOut, MAP)          */
+    uint32_t* flags;    /* device, borrowed: per-cell flag words                      */
+    int32_t   nx, ny, nz_local; /* cells of this partition                            */
+    int32_t   z_halo;           /* ghost z planes per side, 0 (one device) or 1       */
+    int64_t   pitch_y, pitch_z, pitch_q; /* in elements                               */
+    int32_t   z_origin;         /* global z of local plane 0                          */
+    int32_t   gnx, gny, gnz;    /* global box                                         */
+} nlbm_dense_desc;
+
+int         nlbm_abi_version(void);
+const char* nlbm_last_error(void);
+/* number of CUDA devices visible, or -1 (error text in nlbm_last_error) */
+int nlbm_device_count(void);
+
+/* Fills pitch_y/pitch_z/pitch_q of `d` from nx, ny, nz_local, z_halo for an element
+ * of elem_bytes (4|8) and returns the bytes one population FIELD of q components
+ * needs in *pop_bytes and the flag array in *flag_bytes.  Host only.  This is where
+ * the reference decides its pitch: dField_imp.h:67-87.                            */
+int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_bytes, size_t* flag_bytes);
+
+/* ---- problem set-up on the device (RunCavityTwoPop.cu:159-242) ------------------
+ * geom: 0 lid-driven cavity; 1 cavity + solid sphere; 2 flow over sphere (x=0 inlet
+ * treated as moving wall, other faces bounce-back).  sphere = {cx,cy,cz,R}
+ * in global cells or NULL for the default (0.45nx, 0.55ny, 0.5nz, min(n)/5).
+ * Writes the class bits of every plane including ghosts (mask bits cleared).       */
+int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream);
+/* LbmContainers::computeWallNghMask, LbmTools.h:344-376 (bit-exact).  q = 19|27.
+ * Needs valid class bits in the ghost planes.  *d_bad (device int32, may be NULL) is
+ * incremented for every bulk-cell neighbour outside the global domain.             */
+int nlbm_dense_wall_mask(const nlbm_dense_desc* d, int q, int32_t* d_bad, void* stream);
+/* Initial populations of BOTH semantics of the reference set-up: bulk t_k, bounceBack 0,
+ * movingWall -6 t_k ulb (c_k . (1,0,0))   (RunCavityTwoPop.cu:168-206).  Writes d->pop_out. */
+int nlbm_dense_init_pop_f32(const nlbm_dense_desc* d, int q, double ulb, void* stream);
+int nlbm_dense_init_pop_f64(const nlbm_dense_desc* d, int q, double ulb, void* stream);
+
+/* ---- THE HOT PATH: fused pull-stream + BGK collide, one iteration ---------------
+ * LbmContainers::iteration (LbmTools.h:285-325) = pullStream (:99-168) + macroscopic
+ * (:172-195) + collideBgkUnrolled (:199-282); D3Q27: apps/lbmMultiRes/{stream.h:5-49,
+ * collide.h:286-354}.  Reads d->pop_in (+ghost planes), writes bulk cells of d->pop_out
+ * in the z range selected by data_view.  omega as in Config.cpp:105-111.            */
+int nlbm_d3q19_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q19_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
+/* store float / compute double — the reference sweep's "f/d" column */
+int nlbm_d3q19_f32c64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q27_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q27_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
+
+/* LbmContainers::computeRhoAndU, LbmTools.h:384-437 (D3Q19).  rho: [zm][y][x] with the
+ * descriptor's pitches; u: 3 such planes sets, pitch_q apart.                        */
+int nlbm_d3q19_f32_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream);
+int nlbm_d3q19_f64_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream);
+
+/* ---- halo update (dField::newHaloUpdate, dField_imp.h:341-421,548-641) ----------
+ * The reference copies all q planes per direction with one cudaMemcpyPeerAsync each
+ * (DataTransferContainer.h:38-55).  Here one launch moves only the populations that
+ * cross the face (D3Q19: 5 of 19, D3Q27: 9 of 27; `lattice_q` = 0 moves all `ncomp`
+ * components — "grid semantic", used for flags and generic fields).
+ *   dir = +1: src's top boundary plane (local z = nz_local-1) -> dst's lower ghost plane
+ *   dir = -1: src's bottom boundary plane (local z = 0)       -> dst's upper ghost plane
+ * src/dst are device pointers to whole fields with the descriptors' layout; they may live
+ * on different GPUs (peer access enabled by the caller, or a CUDA-IPC mapping): the
+ * kernel then stores straight into the peer's HBM over NVLink.                       */
+int nlbm_dense_halo_push(const nlbm_dense_desc* src_desc, const void* src_field, const nlbm_dense_desc* dst_desc,
+                         void* dst_field, int elem_bytes, int ncomp, int lattice_q, int dir, void* stream);
+/* Staged variant for transports that cannot map peer memory (NCCL send/recv):
+ * pack the crossing populations of one boundary plane into a contiguous buffer and
+ * unpack such a buffer into a ghost plane.  Returns the byte count in *bytes.        */
+int nlbm_dense_halo_pack(const nlbm_dense_desc* d, const void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
+                         void* buffer, size_t* bytes, void* stream);
+int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
+                           const void* buffer, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEON_LBM_H */

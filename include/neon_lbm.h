@@ -82,8 +82,13 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * Memory layout (structure of arrays, one plane set per population):
  *   pop[q][zm][y][x] at  q*pitch_q + zm*pitch_z + y*pitch_y + x      (elements)
  *   zm = z_local + z_halo in [0, nz_local + 2*z_halo)   ghost planes at both ends
- *   pitch_y*sizeof(T) is a multiple of 128 bytes; base pointers 128-byte aligned.
- * The flag array uses the same (zm,y,x) indexing with pitch_y / pitch_z.
+ *   pitch_y*sizeof(T) is a multiple of 128 bytes (nlbm_dense_layout picks 512: one warp
+ *   request of 32 x 16 bytes); base pointers 128-byte aligned.
+ * The flag array uses the same (zm,y,x) indexing with pitch_y / pitch_z.  Behind the
+ * per-cell words the SAME buffer holds a small per-row summary (which 32-cell chunks
+ * contain anything but plain bulk cells) that lets the step kernels skip flag loads;
+ * nlbm_dense_classify / nlbm_dense_wall_mask keep it current, and a caller that writes
+ * flag words itself must call nlbm_dense_flags_commit before stepping.
  * (Reference: unpadded SoA, dField_imp.h:67-87.)                                 */
 typedef struct nlbm_dense_desc {
     void*     pop_in;   /* device, borrowed: populations read  (fIn,  const STENCIL)  */
@@ -113,6 +118,8 @@ int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_byt
  * in global cells or NULL for the default (0.45nx, 0.55ny, 0.5nz, min(n)/5).
  * Writes the class bits of every plane including ghosts (mask bits cleared).       */
 int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream);
+/* Rebuilds the per-row summary from the flag words (after the caller wrote them itself). */
+int nlbm_dense_flags_commit(const nlbm_dense_desc* d, void* stream);
 /* LbmContainers::computeWallNghMask, LbmTools.h:344-376 (bit-exact).  q = 19|27.
  * Needs valid class bits in the ghost planes.  *d_bad (device int32, may be NULL) is
  * incremented for every bulk-cell neighbour outside the global domain.             */

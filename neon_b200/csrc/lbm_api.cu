@@ -1,0 +1,334 @@
+// lbm_api.cu — the C ABI of include/neon_lbm.h: argument checking, layout, dispatch.  No CPU fallback anywhere: every
+// compute entry point needs a CUDA device and fails with NLBM_ERR_CUDA otherwise.
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "lbm_common.cuh"
+#include "lbm_host.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cudaFail(cudaError_t e, const char* what)
+{
+    return fail(NLBM_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+int checkDesc(const nlbm_dense_desc* d, int elemBytes, bool needIn, bool needOut, bool needFlags)
+{
+    if (!d)
+        return fail(NLBM_ERR_INVALID, "null descriptor");
+    if (d->nx <= 0 || d->ny <= 0 || d->nz_local <= 0 || d->z_halo < 0 || d->z_halo > 1)
+        return fail(NLBM_ERR_INVALID, "bad partition size %d x %d x %d (z_halo %d)", d->nx, d->ny, d->nz_local, d->z_halo);
+    if (d->pitch_y < d->nx || d->pitch_y % 32 != 0 || d->pitch_y > INT_MAX)
+        return fail(NLBM_ERR_INVALID, "pitch_y %lld must be a multiple of 32 elements and >= nx", (long long)d->pitch_y);
+    if (d->pitch_z < d->pitch_y * d->ny || d->pitch_z % 32 != 0)
+        return fail(NLBM_ERR_INVALID, "pitch_z %lld too small or misaligned", (long long)d->pitch_z);
+    if (d->pitch_q < d->pitch_z * (d->nz_local + 2 * d->z_halo) || d->pitch_q % 32 != 0)
+        return fail(NLBM_ERR_INVALID, "pitch_q %lld too small or misaligned", (long long)d->pitch_q);
+    if (d->ny > 65535 || d->nz_local + 2 * d->z_halo > 65535)
+        return fail(NLBM_ERR_UNSUPPORTED, "ny and nz_local are limited to 65535");
+    if (needIn && (!d->pop_in || ((uintptr_t)d->pop_in & 127)))
+        return fail(NLBM_ERR_INVALID, "pop_in null or not 128-byte aligned");
+    if (needOut && (!d->pop_out || ((uintptr_t)d->pop_out & 127)))
+        return fail(NLBM_ERR_INVALID, "pop_out null or not 128-byte aligned");
+    if (needFlags && (!d->flags || ((uintptr_t)d->flags & 127)))
+        return fail(NLBM_ERR_INVALID, "flags null or not 128-byte aligned");
+    if (needIn && needOut && d->pop_in == d->pop_out)
+        return fail(NLBM_ERR_INVALID, "pop_in and pop_out alias (the pull scheme needs two fields, LbmIteration.h:38-39)");
+    (void)elemBytes;
+    return NLBM_OK;
+}
+
+int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, double omega, int view, int opts, void* stream)
+{
+    if (int rc = checkDesc(d, elemBytes, true, true, true))
+        return rc;
+    if (view < NLBM_VIEW_STANDARD || view > NLBM_VIEW_BOUNDARY)
+        return fail(NLBM_ERR_INVALID, "bad data view %d", view);
+    const int arith = opts & 0xF;
+    if (arith != NLBM_ARITH_REFERENCE && arith != NLBM_ARITH_FAST)
+        return fail(NLBM_ERR_INVALID, "bad arithmetic mode %d", arith);
+    nlbm::DenseArgs a;
+    a.in = d->pop_in;
+    a.out = d->pop_out;
+    a.flags = d->flags;
+    a.summary = nlbm::summaryPtr(*d);
+    a.nx = d->nx;
+    a.ny = d->ny;
+    a.nzm = d->nz_local + 2 * d->z_halo;
+    a.pitch_y = (int32_t)d->pitch_y;
+    a.pitch_z = d->pitch_z;
+    a.pitch_q = d->pitch_q;
+    a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
+    a.omega = omega;
+    // Views split at stencil radius 1 (both lattices): INTERNAL = local z in [1, nz-1), BOUNDARY = {0, nz-1}
+    // (the reference's BOUNDARY span folds wrongly; this is the intended cover).
+    const int r = 1, nz = d->nz_local;
+    int       nzView = nz;
+    a.zm0 = d->z_halo;
+    a.fold = INT_MAX;
+    a.skip = 0;
+    if (view == NLBM_VIEW_INTERNAL) {
+        a.zm0 = d->z_halo + r;
+        nzView = nz - 2 * r;
+    } else if (view == NLBM_VIEW_BOUNDARY) {
+        if (nz >= 2 * r) {
+            nzView = 2 * r;
+            a.fold = r;
+            a.skip = nz - 2 * r;
+        }
+    }
+    if (nzView <= 0)
+        return NLBM_OK;
+    const int    vec = (opts >> 4) & 0xF;
+    const int    rowsLog2 = (opts >> 8) & 0xF;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t  e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchStepRef(kind, a, nzView, vec, rowsLog2, st)
+                                                   : nlbm::launchStepFast(kind, a, nzView, vec, rowsLog2, st);
+    if (e != cudaSuccess)
+        return cudaFail(e, "dense step launch");
+    return NLBM_OK;
+}
+
+int crossing(int latticeQ, int ncomp, int dir, int* list)
+{
+    int n = 0;
+    if (latticeQ == 0) {
+        for (int q = 0; q < ncomp; ++q)
+            list[n++] = q;
+    } else if (latticeQ == 19) {
+        for (int q = 0; q < 19; ++q)
+            if (nlbm::Lattice<19>::c(q, 2) == dir)
+                list[n++] = q;
+    } else {
+        for (int q = 0; q < 27; ++q)
+            if (nlbm::Lattice<27>::c(q, 2) == dir)
+                list[n++] = q;
+    }
+    return n;
+}
+
+int checkHalo(const nlbm_dense_desc* d, int elemBytes, int ncomp, int latticeQ, int dir)
+{
+    if (int rc = checkDesc(d, elemBytes, false, false, false))
+        return rc;
+    if (elemBytes != 4 && elemBytes != 8)
+        return fail(NLBM_ERR_INVALID, "elem_bytes must be 4 or 8");
+    if (dir != 1 && dir != -1)
+        return fail(NLBM_ERR_INVALID, "dir must be +1 or -1");
+    if (!(latticeQ == 0 || latticeQ == 19 || latticeQ == 27) || ncomp < 1 || ncomp > 27 || (latticeQ && ncomp != latticeQ))
+        return fail(NLBM_ERR_INVALID, "bad component count %d / lattice %d", ncomp, latticeQ);
+    return NLBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int         nlbm_abi_version(void) { return NLBM_ABI_VERSION; }
+const char* nlbm_last_error(void) { return g_err; }
+
+int nlbm_device_count(void)
+{
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaFail(e, "cudaGetDeviceCount");
+        return -1;
+    }
+    return n;
+}
+
+int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_bytes, size_t* flag_bytes)
+{
+    if (!d || d->nx <= 0 || d->ny <= 0 || d->nz_local <= 0 || d->z_halo < 0 || d->z_halo > 1)
+        return fail(NLBM_ERR_INVALID, "bad partition size");
+    if ((elem_bytes != 4 && elem_bytes != 8) || q < 1 || q > 27)
+        return fail(NLBM_ERR_INVALID, "bad element size %d or component count %d", elem_bytes, q);
+    // rows start on 512-byte boundaries: one warp moves 32 x 16 bytes of a row per request
+    d->pitch_y = nlbm::alignUp(d->nx, 512 / elem_bytes);
+    d->pitch_z = d->pitch_y * d->ny;
+    d->pitch_q = d->pitch_z * (d->nz_local + 2 * d->z_halo);
+    if (pop_bytes)
+        *pop_bytes = (size_t)q * (size_t)d->pitch_q * (size_t)elem_bytes;
+    if (flag_bytes) {
+        const int64_t rows = (int64_t)d->ny * (d->nz_local + 2 * d->z_halo);
+        *flag_bytes = (size_t)(nlbm::flagCellWords(*d) + 2 * rows * nlbm::summaryWordsPerRow(d->pitch_y)) * 4;
+    }
+    return NLBM_OK;
+}
+
+int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream)
+{
+    if (int rc = checkDesc(d, 4, false, false, true))
+        return rc;
+    if (geom < 0 || geom > 2)
+        return fail(NLBM_ERR_INVALID, "bad geometry %d", geom);
+    if (d->nx != d->gnx || d->ny != d->gny)
+        return fail(NLBM_ERR_INVALID, "partitions split z only (dGrid_imp.h:32-63): nx,ny must equal gnx,gny");
+    cudaError_t e = nlbm::launchClassify(*d, geom, sphere, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "classify launch");
+}
+
+int nlbm_dense_flags_commit(const nlbm_dense_desc* d, void* stream)
+{
+    if (int rc = checkDesc(d, 4, false, false, true))
+        return rc;
+    cudaError_t e = nlbm::launchSummary(*d, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag summary launch");
+}
+
+int nlbm_dense_wall_mask(const nlbm_dense_desc* d, int q, int32_t* d_bad, void* stream)
+{
+    if (int rc = checkDesc(d, 4, false, false, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchWallMask(*d, q, d_bad, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "wall mask launch");
+}
+
+int nlbm_dense_init_pop_f32(const nlbm_dense_desc* d, int q, double ulb, void* stream)
+{
+    if (int rc = checkDesc(d, 4, false, true, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchInitPop<float>(*d, q, ulb, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "init launch");
+}
+int nlbm_dense_init_pop_f64(const nlbm_dense_desc* d, int q, double ulb, void* stream)
+{
+    if (int rc = checkDesc(d, 8, false, true, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchInitPop<double>(*d, q, ulb, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "init launch");
+}
+
+int nlbm_d3q19_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return stepImpl(nlbm::kD3Q19_F32, 4, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q19_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return stepImpl(nlbm::kD3Q19_F64, 8, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q19_f32c64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return stepImpl(nlbm::kD3Q19_F32C64, 4, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q27_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return stepImpl(nlbm::kD3Q27_F32, 4, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q27_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return stepImpl(nlbm::kD3Q27_F64, 8, d, omega, data_view, opts, stream);
+}
+
+int nlbm_d3q19_f32_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream)
+{
+    if (int rc = checkDesc(d, 4, true, false, true))
+        return rc;
+    if (!rho || !u)
+        return fail(NLBM_ERR_INVALID, "null output");
+    cudaError_t e = nlbm::launchRhoU<float, float>(*d, rho, u, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "rho/u launch");
+}
+int nlbm_d3q19_f64_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream)
+{
+    if (int rc = checkDesc(d, 8, true, false, true))
+        return rc;
+    if (!rho || !u)
+        return fail(NLBM_ERR_INVALID, "null output");
+    cudaError_t e = nlbm::launchRhoU<double, double>(*d, rho, u, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "rho/u launch");
+}
+
+int nlbm_dense_halo_push(const nlbm_dense_desc* s, const void* src_field, const nlbm_dense_desc* t, void* dst_field,
+                         int elem_bytes, int ncomp, int lattice_q, int dir, void* stream)
+{
+    if (int rc = checkHalo(s, elem_bytes, ncomp, lattice_q, dir))
+        return rc;
+    if (int rc = checkHalo(t, elem_bytes, ncomp, lattice_q, dir))
+        return rc;
+    if (!src_field || !dst_field)
+        return fail(NLBM_ERR_INVALID, "null field");
+    if (t->z_halo < 1)
+        return fail(NLBM_ERR_INVALID, "destination partition has no ghost planes");
+    if (s->pitch_y != t->pitch_y || s->pitch_z != t->pitch_z || s->ny != t->ny || s->nx != t->nx)
+        return fail(NLBM_ERR_INVALID, "source and destination planes differ in shape");
+    int             list[27];
+    nlbm::PlaneList pl;
+    pl.n = crossing(lattice_q, ncomp, dir, list);
+    const int64_t zs = dir > 0 ? s->z_halo + s->nz_local - 1 : s->z_halo;
+    const int64_t zd = dir > 0 ? 0 : t->z_halo + t->nz_local;
+    for (int i = 0; i < pl.n; ++i) {
+        pl.src[i] = (list[i] * s->pitch_q + zs * s->pitch_z) * elem_bytes;
+        pl.dst[i] = (list[i] * t->pitch_q + zd * t->pitch_z) * elem_bytes;
+    }
+    cudaError_t e = nlbm::launchPlaneCopy(src_field, dst_field, pl, (size_t)s->pitch_z * elem_bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo push launch");
+}
+
+int nlbm_dense_halo_pack(const nlbm_dense_desc* d, const void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
+                         void* buffer, size_t* bytes, void* stream)
+{
+    if (int rc = checkHalo(d, elem_bytes, ncomp, lattice_q, dir))
+        return rc;
+    int             list[27];
+    nlbm::PlaneList pl;
+    pl.n = crossing(lattice_q, ncomp, dir, list);
+    const size_t planeBytes = (size_t)d->pitch_z * elem_bytes;
+    if (bytes)
+        *bytes = planeBytes * pl.n;
+    if (!buffer)
+        return NLBM_OK;  // size query
+    if (!field)
+        return fail(NLBM_ERR_INVALID, "null field");
+    const int64_t zs = dir > 0 ? d->z_halo + d->nz_local - 1 : d->z_halo;
+    for (int i = 0; i < pl.n; ++i) {
+        pl.src[i] = (list[i] * d->pitch_q + zs * d->pitch_z) * elem_bytes;
+        pl.dst[i] = (int64_t)i * planeBytes;
+    }
+    cudaError_t e = nlbm::launchPlaneCopy(field, buffer, pl, planeBytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo pack launch");
+}
+
+int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
+                           const void* buffer, void* stream)
+{
+    if (int rc = checkHalo(d, elem_bytes, ncomp, lattice_q, dir))
+        return rc;
+    if (!field || !buffer)
+        return fail(NLBM_ERR_INVALID, "null field or buffer");
+    if (d->z_halo < 1)
+        return fail(NLBM_ERR_INVALID, "partition has no ghost planes");
+    int             list[27];
+    nlbm::PlaneList pl;
+    pl.n = crossing(lattice_q, ncomp, dir, list);
+    const size_t  planeBytes = (size_t)d->pitch_z * elem_bytes;
+    const int64_t zd = dir > 0 ? 0 : d->z_halo + d->nz_local;  // data moving up lands in my lower ghost plane
+    for (int i = 0; i < pl.n; ++i) {
+        pl.src[i] = (int64_t)i * planeBytes;
+        pl.dst[i] = (list[i] * d->pitch_q + zd * d->pitch_z) * elem_bytes;
+    }
+    cudaError_t e = nlbm::launchPlaneCopy(buffer, field, pl, planeBytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo unpack launch");
+}
+
+}  // extern "C"

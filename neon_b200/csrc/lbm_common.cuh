@@ -1,0 +1,154 @@
+// lbm_common.cuh — shared device/host helpers of the sm_100a LBM kernels.
+//
+// Lattice tables follow the reference numbering exactly:
+//   D3Q19: benchmarks/lbm-lid-driven-cavity-flow/src/D3Q19.h:23-44 (velocities), :112-132 (weights);
+//          opposite of q is q+10 / q-10, rest population is 9.
+//   D3Q27: apps/lbmMultiRes/lattice.h:15-77 (rest population is 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/neon_lbm.h"
+
+namespace nlbm {
+
+// ---------------------------------------------------------------- lattices
+template <int Q>
+struct Lattice;
+
+template <>
+struct Lattice<19>
+{
+    static constexpr int Q = 19;
+    static constexpr int REST = 9;
+    __host__ __device__ static constexpr int c(int q, int d)
+    {
+        constexpr int t[19][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1},
+                                  {0, -1, -1}, {0, -1, 1}, {0, 0, 0},  {1, 0, 0},  {0, 1, 0},   {0, 0, 1},  {1, 1, 0},
+                                  {1, -1, 0},  {1, 0, 1},  {1, 0, -1}, {0, 1, 1},  {0, 1, -1}};
+        return t[q][d];
+    }
+    __host__ __device__ static constexpr int opp(int q) { return q == 9 ? 9 : (q < 9 ? q + 10 : q - 10); }
+    __host__ __device__ static constexpr double w(int q)
+    {
+        return q == 9 ? 1. / 3. : (((q % 10) < 3) ? 1. / 18. : 1. / 36.);
+    }
+};
+
+template <>
+struct Lattice<27>
+{
+    static constexpr int Q = 27;
+    static constexpr int REST = 0;
+    __host__ __device__ static constexpr int c(int q, int d)
+    {
+        constexpr int t[27][3] = {{0, 0, 0},   {0, 0, -1},   {0, 0, 1},   {0, -1, 0},  {0, -1, -1}, {0, -1, 1}, {0, 1, 0},
+                                  {0, 1, -1},  {0, 1, 1},    {-1, 0, 0},  {-1, 0, -1}, {-1, 0, 1},  {-1, -1, 0}, {-1, -1, -1},
+                                  {-1, -1, 1}, {-1, 1, 0},   {-1, 1, -1}, {-1, 1, 1},  {1, 0, 0},   {1, 0, -1}, {1, 0, 1},
+                                  {1, -1, 0},  {1, -1, -1},  {1, -1, 1},  {1, 1, 0},   {1, 1, -1},  {1, 1, 1}};
+        return t[q][d];
+    }
+    __host__ __device__ static constexpr int opp(int q)
+    {
+        constexpr int t[27] = {0,  2,  1,  6,  8,  7,  3,  5,  4,  18, 20, 19, 24, 26,
+                               25, 21, 23, 22, 9,  11, 10, 15, 17, 16, 12, 14, 13};
+        return t[q];
+    }
+    __host__ __device__ static constexpr double w(int q)
+    {
+        const int n = (c(q, 0) != 0) + (c(q, 1) != 0) + (c(q, 2) != 0);
+        return n == 0 ? 8.0 / 27.0 : (n == 1 ? 2.0 / 27.0 : (n == 2 ? 1.0 / 54.0 : 1.0 / 216.0));
+    }
+};
+
+// ---------------------------------------------------------------- flag words
+constexpr uint32_t kMaskBits = NLBM_FLAG_MASK_BITS;
+constexpr uint32_t kPlainBulk = (uint32_t)NLBM_BULK << NLBM_FLAG_CLASS_SHIFT;  // bulk, no wall neighbour
+__host__ __device__ inline uint32_t flagClass(uint32_t f) { return (f >> NLBM_FLAG_CLASS_SHIFT) & 3u; }
+__host__ __device__ inline bool     flagIsBulk(uint32_t f) { return flagClass(f) == (uint32_t)NLBM_BULK; }
+
+// Row summary that lives behind the per-cell flag words (same buffer): for every row (zm, y) and every
+// group of 32 chunks (chunk = 32 consecutive cells in x) one uint2 {special, bulk}:
+//   bit i of .x set <=> chunk i holds a cell that is not "plain bulk" (non-bulk, wall bits set, or x >= nx)
+//   bit i of .y set <=> chunk i holds at least one bulk cell
+// The step kernels skip flag loads and the fix-up code for chunks whose special bit is clear.
+constexpr int kChunk = 32;
+__host__ __device__ inline int64_t summaryWordsPerRow(int64_t pitch_y) { return (pitch_y / kChunk + 31) / 32; }
+__host__ __device__ inline int64_t alignUp(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int64_t flagCellWords(const nlbm_dense_desc& d)
+{
+    return alignUp((int64_t)(d.nz_local + 2 * d.z_halo) * d.pitch_z, 32);
+}
+inline __host__ __device__ const uint2* summaryPtr(const nlbm_dense_desc& d)
+{
+    return reinterpret_cast<const uint2*>(d.flags + flagCellWords(d));
+}
+
+// ---------------------------------------------------------------- kernel arguments (by value)
+struct DenseArgs
+{
+    const void* in;
+    void*       out;
+    const uint32_t* flags;
+    const uint2*    summary;
+    int32_t nx, ny, nzm;  // nzm = nz_local + 2*z_halo memory planes
+    int32_t pitch_y;      // elements
+    int64_t pitch_z, pitch_q;
+    int32_t wpr;          // summary words per row
+    int32_t zm0;          // first memory plane of the view
+    int32_t fold, skip;   // view planes >= fold are shifted by skip (BOUNDARY view: two slabs)
+    double  omega;
+};
+
+// ---------------------------------------------------------------- vector access
+template <typename T, int VEC>
+struct Vec;
+template <>
+struct Vec<float, 1>
+{
+    using type = float;
+};
+template <>
+struct Vec<float, 2>
+{
+    using type = float2;
+};
+template <>
+struct Vec<float, 4>
+{
+    using type = float4;
+};
+template <>
+struct Vec<double, 1>
+{
+    using type = double;
+};
+template <>
+struct Vec<double, 2>
+{
+    using type = double2;
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void ldVec(const T* __restrict__ p, T (&v)[VEC])
+{
+    using V = typename Vec<T, VEC>::type;
+    const V t = __ldg(reinterpret_cast<const V*>(p));
+    const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        v[i] = e[i];
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void stVec(T* __restrict__ p, const T (&v)[VEC])
+{
+    using V = typename Vec<T, VEC>::type;
+    V  t;
+    T* e = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        e[i] = v[i];
+    __stcs(reinterpret_cast<V*>(p), t);  // streaming store: not re-read before the next iteration
+}
+
+}  // namespace nlbm

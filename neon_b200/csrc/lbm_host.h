@@ -1,0 +1,36 @@
+// lbm_host.h — internal declarations shared by the translation units of libneon_lbm.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/neon_lbm.h"
+
+namespace nlbm {
+
+enum StepKind { kD3Q19_F32 = 0, kD3Q19_F64 = 1, kD3Q19_F32C64 = 2, kD3Q27_F32 = 3, kD3Q27_F64 = 4 };
+
+struct DenseArgs;
+// lbm_step_ref.cu (-fmad=false) / lbm_step_fast.cu
+cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st);
+cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st);
+
+// lbm_setup.cu
+cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st);
+cudaError_t launchClassify(const nlbm_dense_desc& d, int geom, const double* sphere, cudaStream_t st);
+cudaError_t launchWallMask(const nlbm_dense_desc& d, int q, int32_t* d_bad, cudaStream_t st);
+template <typename S>
+cudaError_t launchInitPop(const nlbm_dense_desc& d, int q, double ulb, cudaStream_t st);
+template <typename S, typename C>
+cudaError_t launchRhoU(const nlbm_dense_desc& d, void* rho, void* u, cudaStream_t st);
+
+// lbm_halo.cu
+struct PlaneList
+{
+    int     n;
+    int64_t src[27];  // byte offsets
+    int64_t dst[27];
+};
+cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, size_t planeBytes, cudaStream_t st);
+
+}  // namespace nlbm

@@ -1,0 +1,125 @@
+"""The LBM hot path behind the reference's names.
+
+  LbmContainers.iteration          benchmarks/lbm-lid-driven-cavity-flow/src/LbmTools.h:285-325
+  LbmContainers.computeWallNghMask LbmTools.h:344-376
+  LbmContainers.computeRhoAndU     LbmTools.h:384-437
+  LbmIteration                     src/LbmIteration.h:19-101 (two pre-built Skeletons, parity flip, no field swap)
+  getLbmParameters                 src/Config.cpp:105-111
+
+Every container is one call into libneon_lbm.so (hand-written sm_100a kernels); nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi as capi
+from .backend import Runtime
+from .containers import Access, Container, Pattern, Token
+from .dgrid import DataView, FlagField, StencilSemantic, TransferMode, dField
+from .skeleton import Occ, Options, Skeleton
+
+
+def omega_from_re(n: int, re: float = 100.0, ulb: float = 0.04) -> float:
+    """Config::helpSetLbmParameters, Config.cpp:105-111 (clength = N - 2)"""
+    nu = ulb * float(n - 2) / re
+    return 1.0 / (3.0 * nu + 0.5)
+
+
+def _step_symbol(q: int, store: np.dtype, compute: Optional[np.dtype]) -> str:
+    store = np.dtype(store)
+    compute = store if compute is None else np.dtype(compute)
+    if store == np.float32 and compute == np.float32:
+        return f"nlbm_d3q{q}_f32_dense_step"
+    if store == np.float64 and compute == np.float64:
+        return f"nlbm_d3q{q}_f64_dense_step"
+    if q == 19 and store == np.float32 and compute == np.float64:
+        return "nlbm_d3q19_f32c64_dense_step"
+    raise ValueError(f"unsupported D3Q{q} store/compute pair {store}/{compute}")
+
+
+class LbmContainers:
+    @staticmethod
+    def iteration(stencilSemantic: StencilSemantic, fIn: dField, fOut: dField, cellTypeField: FlagField, omega: float,
+                  lattice_q: int = 19, compute=None, arith: int = capi.ARITH_FAST, opts: int = 0,
+                  halo_transport: str = "auto") -> Container:
+        """One fused pull-stream + BGK collide over the cells of ``dataView``.  fIn is loaded as const STENCIL (needs
+        its ghost planes current), fOut as MAP write, the flags as MAP read (LbmTools.h:296-299)."""
+        if fIn is fOut:
+            raise capi.NeonException("LbmContainers.iteration", capi.ERR_INVALID, "fIn and fOut must be two fields")
+        grid = fIn.grid
+        sym = _step_symbol(lattice_q, fIn.dtype, compute)
+        if fIn.cardinality != lattice_q or fOut.cardinality != lattice_q or fOut.dtype != fIn.dtype:
+            raise capi.NeonException("LbmContainers.iteration", capi.ERR_INVALID, "population fields do not match the lattice")
+        desc = grid.desc(fIn, fOut, cellTypeField)
+        fn = getattr(capi.lib(), sym)
+        bk = grid.backend
+        o = int(arith) | int(opts)
+
+        def launch(streamIdx: int, dataView: DataView) -> None:
+            capi.check(fn(C.byref(desc), omega, dataView.value, o, bk.streamHandle(streamIdx)), sym)
+
+        c = Container(f"LBM_iteration_D3Q{lattice_q}",
+                      [Token(fIn, Access.READ, Pattern.STENCIL, stencilSemantic, lattice_q),
+                       Token(fOut, Access.WRITE, Pattern.MAP), Token(cellTypeField, Access.READ, Pattern.MAP)], launch)
+        c.halo_transport = halo_transport
+        return c
+
+    @staticmethod
+    def computeWallNghMask(infoInField: FlagField, infoOutpeField: FlagField, lattice_q: int = 19) -> Container:
+        if infoInField is not infoOutpeField:
+            raise capi.NeonException("computeWallNghMask", capi.ERR_UNSUPPORTED,
+                                     "the mask is built in place, as RunCavityTwoPop.cu:239 runs it")
+
+        def launch(streamIdx: int, dataView: DataView) -> None:
+            infoInField.computeWallNghMask(lattice_q, streamIdx)
+
+        return Container("computeWallNghMask", [Token(infoInField, Access.READ, Pattern.STENCIL),
+                                                Token(infoOutpeField, Access.WRITE, Pattern.MAP)], launch)
+
+    @staticmethod
+    def computeRhoAndU(fIn: dField, cellTypeField: FlagField, rho: dField, u: dField) -> Container:
+        grid = fIn.grid
+        sym = "nlbm_d3q19_f32_dense_rho_u" if fIn.dtype == np.float32 else "nlbm_d3q19_f64_dense_rho_u"
+        if fIn.cardinality != 19 or rho.cardinality != 1 or u.cardinality != 3 or rho.dtype != fIn.dtype or u.dtype != fIn.dtype:
+            raise capi.NeonException("computeRhoAndU", capi.ERR_INVALID, "rho must have 1 and u 3 components of fIn's type")
+        desc = grid.desc(fIn, None, cellTypeField)
+        fn = getattr(capi.lib(), sym)
+        bk = grid.backend
+
+        def launch(streamIdx: int, dataView: DataView) -> None:
+            capi.check(fn(C.byref(desc), rho.data.data_ptr(), u.data.data_ptr(), bk.streamHandle(streamIdx)), sym)
+
+        return Container("LBM_macroscopic", [Token(fIn, Access.READ, Pattern.STENCIL), Token(rho, Access.WRITE, Pattern.MAP),
+                                             Token(u, Access.WRITE, Pattern.MAP)], launch)
+
+
+class LbmIteration:
+    """LbmIterationD3Q19 (LbmIteration.h:19-101), for D3Q19 and D3Q27: skeleton 0 streams pop0 -> pop1, skeleton 1
+    pop1 -> pop0; run() executes skeleton[parity] and flips the parity."""
+
+    def __init__(self, stencilSemantic: StencilSemantic, occ: Occ, transfer: TransferMode, fInField: dField,
+                 fOutField: dField, flagField: FlagField, omega: float, lattice_q: int = 19, compute=None,
+                 arith: int = capi.ARITH_FAST, opts: int = 0, halo_transport: str = "auto", graph: bool = False):
+        self.pop = [fInField, fOutField]
+        self.flag, self.omega, self.parity = flagField, omega, 0
+        bk = fInField.grid.backend
+        self.lbmTwoPop = []
+        for a, b in ((0, 1), (1, 0)):
+            c = LbmContainers.iteration(stencilSemantic, self.pop[a], self.pop[b], flagField, omega, lattice_q, compute,
+                                        arith, opts, halo_transport)
+            sk = Skeleton(bk)
+            sk.sequence([c], f"LBM_{a}{b}", Options(occ, transfer), graph=graph)
+            self.lbmTwoPop.append(sk)
+
+    def run(self) -> None:
+        self.lbmTwoPop[self.parity].run()
+        self.parity ^= 1
+
+    def getInput(self) -> dField:
+        return self.pop[self.parity]
+
+    def getOutput(self) -> dField:
+        return self.pop[self.parity ^ 1]

@@ -341,7 +341,11 @@ __global__ void __launch_bounds__(kStepThreads) k_dense_step(const DenseArgs a)
     }
 
     T* out0 = reinterpret_cast<T*>(a.out) + cellOff;
-    if (!special) {
+    bool allBulk = true;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        allBulk = allBulk && flagIsBulk(fl[i]);
+    if (allBulk) {  // the common case, also for wall-adjacent cells: full 16-byte stores
 #pragma unroll
         for (int q = 0; q < Q; ++q)
             stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);

@@ -58,6 +58,16 @@ def partition_z(nz: int, n: int) -> Tuple[List[int], List[int]]:
 _TORCH_DT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
 
 
+def _aligned_zeros(n: int, dtype: torch.dtype, device: torch.device, align: int = 512) -> torch.Tensor:
+    """Zeroed flat tensor whose base address is ``align``-byte aligned (CUDA allocations already are; host ones not)."""
+    if device.type == "cuda":
+        return torch.zeros(n, dtype=dtype, device=device)
+    item = torch.empty((), dtype=dtype).element_size()
+    raw = torch.zeros(n + align // item, dtype=dtype)
+    off = (-raw.data_ptr() % align) // item
+    return raw[off:off + n]
+
+
 class dGrid:
     def __init__(self, backend: Backend, dim: Sequence[int], stencil_radius: int = 1,
                  partition: Optional[Tuple[int, int]] = None):
@@ -135,7 +145,7 @@ class dField(_FieldBase):
         self.elem_bytes = dtype.itemsize
         self._desc, pop_bytes, _ = grid.layout(cardinality, self.elem_bytes)
         self.pitch_y, self.pitch_z, self.pitch_q = self._desc.pitch_y, self._desc.pitch_z, self._desc.pitch_q
-        self.data = torch.zeros(pop_bytes // self.elem_bytes, dtype=_TORCH_DT[dtype], device=grid.backend.device)
+        self.data = _aligned_zeros(pop_bytes // self.elem_bytes, _TORCH_DT[dtype], grid.backend.device)
         self.view4 = self.data.view(cardinality, grid.nzm, grid.dim[1], self.pitch_y)
         self._halo_buffers = {}
 
@@ -202,7 +212,7 @@ class FlagField(_FieldBase):
         self.cardinality, self.elem_bytes = 1, 4
         self._desc, _, flag_bytes = grid.layout(1, pop_elem_bytes)  # flags share the populations' pitch
         self.pitch_y, self.pitch_z = self._desc.pitch_y, self._desc.pitch_z
-        self.words = torch.zeros(flag_bytes // 4, dtype=torch.int32, device=grid.backend.device)
+        self.words = _aligned_zeros(flag_bytes // 4, torch.int32, grid.backend.device)
         self.cells = self.words[: grid.nzm * self.pitch_z].view(grid.nzm, grid.dim[1], self.pitch_y)
 
     def _d(self) -> capi.DenseDesc:

@@ -48,7 +48,10 @@ def parse():
     ap.add_argument("--arith", default="fast", choices=["fast", "reference"])
     ap.add_argument("--occ", default="standard", choices=["none", "standard"])
     ap.add_argument("--transport", default="auto", choices=["auto", "packed", "views", "ipc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "tma"])
     ap.add_argument("--vec", type=int, default=0)
+    ap.add_argument("--tma-l2promo", type=int, default=0)
+    ap.add_argument("--tma-groups", type=int, default=0)
     ap.add_argument("--rows-log2", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -196,6 +199,7 @@ def main():
 
     import neon_b200 as nb
     from neon_b200 import problems as P
+    from neon_b200._capi import opt_tma as capi_opt_tma
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +218,8 @@ def main():
     cells = dim[0] * dim[1] * dim[2]
     omega = nb.omega_from_re(dim[0])
     arith = nb.ARITH_FAST if args.arith == "fast" else nb.ARITH_REFERENCE
-    opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2)
+    opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[args.kernel]) \
+        | capi_opt_tma(args.tma_l2promo, args.tma_groups)
     occ = nb.Occ.standard if args.occ == "standard" else nb.Occ.none
 
     bk = nb.Backend()
@@ -305,7 +310,6 @@ def main():
                             pin_memory=(world == 1)) if world == 1 else None
         if world == 1:
             pop_np = pop_h.numpy()
-            L = P.lattice(q)
             full = P.host_populations(q, cls[:3], dtype)  # pattern of three planes: bottom wall, interior, (reused)
             for k in range(q):
                 pop_np[k, 0] = full[k, 0]
@@ -342,7 +346,7 @@ def main():
         line = {"metric": f"LBM MLUPS (D3Q{q} {'fp32' if dtype.itemsize == 4 else 'fp64'})", "value": mlups, "unit": "MLUPS",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32" if dtype.itemsize == 4 else "f64", "data": "synthetic",
-                "config": {"workload": wl["name"], "dim": list(dim), "lattice": f"D3Q{q}", "arith": args.arith,
+                "config": {"workload": wl["name"], "dim": list(dim), "lattice": f"D3Q{q}", "arith": args.arith, "kernel": args.kernel,
                            "occ": args.occ if world > 1 else "n/a (1 partition)", "halo_transport": args.transport if world > 1 else "n/a",
                            "l2": "inputs exceed L2 (two population fields of %.1f GB per GPU)" % (q * cells_rank * dtype.itemsize / 1e9),
                            "partition": f"z-slabs of {grid.nz_local} planes" if world > 1 else "single partition"},

@@ -74,6 +74,16 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * log2 of rows per block, 0 = default).  Never changes results.                  */
 #define NLBM_OPT_VEC(v) (((v)&0xF) << 4)
 #define NLBM_OPT_ROWS_LOG2(r) (((r)&0xF) << 8)
+/* bits 12..15: kernel — 0 library default, 1 direct (aligned 16-byte loads + warp shuffles for the x shift),
+ * 2 persistent TMA-fed (cp.async.bulk.tensor tiles staged in shared memory, mbarrier ring).               */
+#define NLBM_OPT_KERNEL(k) (((k)&0xF) << 12)
+/* experiment knobs of the TMA kernel (never change results): bits 16..17 L2 promotion of the tensor maps (0 256 B,
+ * 1 128 B, 2 64 B, 3 none), bits 18..19 consumer groups per CTA (0 = default 3).                            */
+#define NLBM_OPT_TMA_L2PROMO(p) (((p)&0x3) << 16)
+#define NLBM_OPT_TMA_GROUPS(g) (((g)&0x3) << 18)
+#define NLBM_KERNEL_AUTO 0
+#define NLBM_KERNEL_DIRECT 1
+#define NLBM_KERNEL_TMA 2
 
 /* Dense (dGrid) partition descriptor: one z-slab of the global box on one GPU.
  * Replaces what the reference kernel receives by value: dSpan {dataView, zHalo,

@@ -3,7 +3,8 @@
 Only what the path needs: the C-ABI kernel library (csrc/ -> lib/libneon_lbm.so, include/neon_lbm.h) and the host-side
 mirror of the reference interface for it (Backend, dGrid/dField, Container, Skeleton with OCC, LbmIteration).
 """
-from ._capi import (ARITH_FAST, ARITH_REFERENCE, BOUNCE_BACK, BULK, MOVING_WALL, UNDEFINED, NeonException, opt_rows_log2,
+from ._capi import (ARITH_FAST, ARITH_REFERENCE, BOUNCE_BACK, BULK, KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, MOVING_WALL, UNDEFINED,
+                    NeonException, opt_kernel, opt_rows_log2,
                     opt_vec)
 from .backend import Backend, Runtime
 from .containers import Access, Container, Pattern, Token

@@ -28,6 +28,17 @@ def opt_rows_log2(r: int) -> int:
     return (r & 0xF) << 8
 
 
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+
+
+def opt_kernel(k: int) -> int:
+    return (k & 0xF) << 12
+
+
+def opt_tma(l2promo: int = 0, groups: int = 0) -> int:
+    return ((l2promo & 3) << 16) | ((groups & 3) << 18)
+
+
 class NeonException(RuntimeError):
     """Counterpart of Neon::NeonException (libNeonCore/include/Neon/core/types/Exceptions.h:19-24): every non-zero
     status of the C layer is converted into this, as the reference does for every failed CUDA call."""

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda.h>
+
 #include "lbm_common.cuh"
 #include "lbm_host.h"
 
@@ -51,6 +53,81 @@ int checkDesc(const nlbm_dense_desc* d, int elemBytes, bool needIn, bool needOut
     return NLBM_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encodeTiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool          tried = false;
+    if (!tried) {
+        void*                           p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        tried = true;
+    }
+    return fn;
+}
+
+// 4-D map (x, y, memory plane, population) over a SoA population field; box = one tile of one population
+CUtensorMapL2promotion l2Promotion(int sel)
+{
+    switch (sel) {
+        case 1: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        case 2: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+        case 3: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        default: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
+}
+
+// 3-D map (x, y, memory plane) over the flag words
+bool makeFlagMap(CUtensorMap* m, const nlbm_dense_desc* d, int tx, int ty, int promo)
+{
+    EncodeTiledFn enc = encodeTiled();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)d->pitch_y, (cuuint64_t)d->ny, (cuuint64_t)(d->nz_local + 2 * d->z_halo)};
+    const cuuint64_t strides[2] = {(cuuint64_t)d->pitch_y * 4, (cuuint64_t)d->pitch_z * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)tx, (cuuint32_t)ty, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d->flags, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, l2Promotion(promo), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool makePopMap(CUtensorMap* m, const nlbm_dense_desc* d, int q, int elemBytes, int tx, int ty, int promo)
+{
+    EncodeTiledFn enc = encodeTiled();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)d->nx, (cuuint64_t)d->ny, (cuuint64_t)(d->nz_local + 2 * d->z_halo), (cuuint64_t)q};
+    const cuuint64_t strides[3] = {(cuuint64_t)d->pitch_y * elemBytes, (cuuint64_t)d->pitch_z * elemBytes,
+                                   (cuuint64_t)d->pitch_q * elemBytes};
+    const cuuint32_t box[4] = {(cuuint32_t)tx, (cuuint32_t)ty, 1, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, elemBytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, d->pop_in, dims,
+                     strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2Promotion(promo),
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+int smCount()
+{
+    static int sms[64] = {0};
+    int        dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 0;
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return 0;
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
+
 int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, double omega, int view, int opts, void* stream)
 {
     if (int rc = checkDesc(d, elemBytes, true, true, true))
@@ -92,11 +169,37 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     }
     if (nzView <= 0)
         return NLBM_OK;
-    const int    vec = (opts >> 4) & 0xF;
-    const int    rowsLog2 = (opts >> 8) & 0xF;
+    nlbm::StepLaunch l;
+    l.nzView = nzView;
+    l.vec = (opts >> 4) & 0xF;
+    l.rowsLog2 = (opts >> 8) & 0xF;
+    l.tmapA = nullptr;
+    l.tmapB = nullptr;
+    l.tmapF = nullptr;
+    l.groups = (opts >> 18) & 0x3;
+    l.numSms = 0;
+    const int   kernelSel = (opts >> 12) & 0xF;  // 0 auto, 1 direct loads, 2 TMA-fed persistent
+    const int   q = (kind == nlbm::kD3Q27_F32 || kind == nlbm::kD3Q27_F64) ? 27 : 19;
+    CUtensorMap tmapA, tmapB, tmapF;
+    const int   promo = (opts >> 16) & 0x3;
+    if (kernelSel == 0 || kernelSel == 2) {
+        int tx, ty;
+        nlbm::tmaTileShape(elemBytes, d->nx, &tx, &ty);
+        const int sms = smCount();
+        if (sms > 0 && makePopMap(&tmapA, d, q, elemBytes, tx, ty, promo) &&
+            makePopMap(&tmapB, d, q, elemBytes, tx + 16 / elemBytes, ty, promo) && makeFlagMap(&tmapF, d, tx, ty, promo)) {
+            l.tmapA = &tmapA;
+            l.tmapB = &tmapB;
+            l.tmapF = &tmapF;
+            l.numSms = sms;
+        } else if (kernelSel == 2) {
+            return fail(NLBM_ERR_CUDA, "cannot build the TMA descriptor (cuTensorMapEncodeTiled unavailable or refused)");
+        }
+    } else if (kernelSel != 1) {
+        return fail(NLBM_ERR_INVALID, "bad kernel selector %d", kernelSel);
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t  e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchStepRef(kind, a, nzView, vec, rowsLog2, st)
-                                                   : nlbm::launchStepFast(kind, a, nzView, vec, rowsLog2, st);
+    cudaError_t  e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchStepRef(kind, a, l, st) : nlbm::launchStepFast(kind, a, l, st);
     if (e != cudaSuccess)
         return cudaFail(e, "dense step launch");
     return NLBM_OK;

@@ -12,8 +12,20 @@ enum StepKind { kD3Q19_F32 = 0, kD3Q19_F64 = 1, kD3Q19_F32C64 = 2, kD3Q27_F32 = 
 
 struct DenseArgs;
 // lbm_step_ref.cu (-fmad=false) / lbm_step_fast.cu
-cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st);
-cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st);
+// tmapA != nullptr selects the TMA-fed persistent kernel (lbm_step_tma.cuh), else the direct kernel (lbm_step.cuh)
+struct StepLaunch
+{
+    int         nzView, vec, rowsLog2;
+    const void* tmapA;  // CUtensorMap over pop_in with box (TX, TY), or nullptr
+    const void* tmapB;  // same with box (TX + 16 B, TY): populations with c_x != 0
+    const void* tmapF;  // 3-D map over the flag words, box (TX, TY, 1)
+    int         groups; // consumer groups of the TMA kernel (0 = default)
+    int         numSms;
+};
+cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
+cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
+// tile width / rows of the TMA kernel for a population of elemBytes and a row of nx cells
+void tmaTileShape(int elemBytes, int nx, int* tx, int* ty);
 
 // lbm_setup.cu
 cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st);

@@ -272,6 +272,55 @@ __device__ __forceinline__ void fixAll(std::integer_sequence<int, Qs...>, const 
     (fixOne<L, Qs, T>(cell, a, m, f[Qs][i]), ...);
 }
 
+// Wall fix-ups, collision and stores of the VEC cells one thread owns (shared by the direct and the TMA kernel).
+template <class COL, typename T, int VEC>
+__device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
+                                            const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC])
+{
+    constexpr int Q = COL::Q;
+    using L = Lattice<Q>;
+    if (special) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const uint32_t m = fl[i] & kMaskBits;
+            if (m != 0 && flagIsBulk(fl[i]))
+                fixAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0 + i, a, m, i, f);
+        }
+    }
+
+    const typename COL::Compute omega = (typename COL::Compute)a.omega;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        T p[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            p[q] = f[q][i];
+        COL::run(p, omega);
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            f[q][i] = p[q];
+    }
+
+    bool allBulk = true;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        allBulk = allBulk && flagIsBulk(fl[i]);
+    if (allBulk) {  // the common case, also for wall-adjacent cells: full 16-byte stores
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            if (flagIsBulk(fl[i])) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    __stcs(out0 + q * a.pitch_q + i, f[q][i]);
+            }
+        }
+    }
+}
+
 // =============================================================== the kernel
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
 template <class COL, typename T, int VEC>
@@ -318,47 +367,7 @@ __global__ void __launch_bounds__(kStepThreads) k_dense_step(const DenseArgs a)
     T f[Q][VEC];
     pullAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, lane, f);
 
-    if (special) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const uint32_t m = fl[i] & kMaskBits;
-            if (m != 0 && flagIsBulk(fl[i]))
-                fixAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0 + i, a, m, i, f);
-        }
-    }
-
-    const typename COL::Compute omega = (typename COL::Compute)a.omega;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        T p[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            p[q] = f[q][i];
-        COL::run(p, omega);
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            f[q][i] = p[q];
-    }
-
-    T* out0 = reinterpret_cast<T*>(a.out) + cellOff;
-    bool allBulk = true;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i)
-        allBulk = allBulk && flagIsBulk(fl[i]);
-    if (allBulk) {  // the common case, also for wall-adjacent cells: full 16-byte stores
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            if (flagIsBulk(fl[i])) {
-#pragma unroll
-                for (int q = 0; q < Q; ++q)
-                    __stcs(out0 + q * a.pitch_q + i, f[q][i]);
-            }
-        }
-    }
+    finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
 }
 
 // =============================================================== host launcher

@@ -71,6 +71,12 @@ CASES = [
     (19, np.float32, None, (40, 24, 20), 1, 12),
     (19, np.float32, None, (130, 9, 7), 0, 6),      # nx beyond one warp segment, ragged tail
     (19, np.float32, None, (3, 3, 3), 0, 3),        # a single bulk cell
+    (19, np.float32, None, (300, 7, 5), 0, 4),      # wider than one TMA tile, ragged in x and y
+    (19, np.float64, None, (270, 5, 6), 1, 4),
+    (19, np.float32, None, (300, 70, 40), 1, 3),    # ~2000 TMA tiles: every CTA's stage ring wraps several times
+    (27, np.float64, None, (300, 40, 44), 1, 3),
+    (27, np.float32, None, (200, 50, 40), 2, 3),
+    (19, np.float64, None, (260, 48, 40), 2, 3),
     (19, np.float64, None, (33, 17, 12), 1, 10),
     (19, np.float32, np.float64, (36, 20, 16), 1, 8),
     (27, np.float32, None, (40, 24, 20), 1, 10),
@@ -88,14 +94,16 @@ def test_parity_with_oracle(nb, bk, oracle, q, store, compute, dim, geom, iters)
     pop = oracle.init_pop(q, cls, store)
     omega = oracle.omega_cavity(max(dim))
     ref = oracle.run(q, pop, cls, mask, omega, iters, compute)
-    out, flag = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, compute)
-    assert np.array_equal(flag.masks(), mask), "wall masks must be bit-exact"
-    assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), "REFERENCE arithmetic must be bit-exact"
-    fast, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_FAST, compute)
-    assert rel_err(fast, ref) < REL_TOL[np.dtype(store)]
-    # every vector width computes the same bits
+    for kern in (nb.KERNEL_TMA, nb.KERNEL_DIRECT):  # both kernels: same bits as the reference
+        out, flag = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, compute, opts=nb.opt_kernel(kern))
+        assert np.array_equal(flag.masks(), mask), "wall masks must be bit-exact"
+        assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), f"REFERENCE arithmetic must be bit-exact (kernel {kern})"
+        fast, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_FAST, compute, opts=nb.opt_kernel(kern))
+        assert rel_err(fast, ref) < REL_TOL[np.dtype(store)]
+    # every vector width of the direct kernel computes the same bits
     for vec in (1, 2):
-        v, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, compute, opts=nb.opt_vec(vec))
+        v, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, compute,
+                        opts=nb.opt_vec(vec) | nb.opt_kernel(nb.KERNEL_DIRECT))
         assert np.array_equal(v.view(np.uint8), ref.view(np.uint8)), f"vec={vec}"
 
 
@@ -139,14 +147,14 @@ def test_views_tile_the_partition(nb, bk, oracle):
     """INTERNAL + BOUNDARY == STANDARD, bit for bit, on a slab whose boundary planes hold bulk cells (BOUNDARY must
     cover z = 0 and z = nz-1)."""
     from neon_b200 import problems as P
-    for part in ((0, 3), (1, 3), (2, 3)):
+    for part, kern in (((0, 3), nb.KERNEL_TMA), ((1, 3), nb.KERNEL_TMA), ((2, 3), nb.KERNEL_DIRECT), ((1, 3), nb.KERNEL_DIRECT)):
         grid = nb.dGrid(bk, (40, 24, 21), partition=part)
         pop0, pop1, flag = P.setup_device(grid, 19, np.float32, 1)
         pop0.data.uniform_(0.01, 0.1)  # ghost planes included: any data will do for this identity
         pop2 = grid.newField("pop2", 19, np.float32)
         pop2.data.copy_(pop1.data)
-        a = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop0, pop1, flag, 1.3)
-        b = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop0, pop2, flag, 1.3)
+        a = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop0, pop1, flag, 1.3, opts=nb.opt_kernel(kern))
+        b = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop0, pop2, flag, 1.3, opts=nb.opt_kernel(kern))
         a.run(0, nb.DataView.STANDARD)
         b.run(0, nb.DataView.INTERNAL)
         bk.syncAll()

@@ -81,6 +81,9 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * 1 128 B, 2 64 B, 3 none), bits 18..19 consumer groups per CTA (0 = default 3).                            */
 #define NLBM_OPT_TMA_L2PROMO(p) (((p)&0x3) << 16)
 #define NLBM_OPT_TMA_GROUPS(g) (((g)&0x3) << 18)
+/* bit 20 (direct kernel): fetch the flag words together with the populations (+4 B/cell) instead of consulting the row
+ * summary first — one dependent memory round trip less for warps that touch walls.                              */
+#define NLBM_OPT_FLAGS_ALWAYS (1 << 20)
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2

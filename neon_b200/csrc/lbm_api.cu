@@ -150,6 +150,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.pitch_q = d->pitch_q;
     a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
     a.omega = omega;
+    a.flagsAlways = (opts >> 20) & 1;
     // Views split at stencil radius 1 (both lattices): INTERNAL = local z in [1, nz-1), BOUNDARY = {0, nz-1}
     // (the reference's BOUNDARY span folds wrongly; this is the intended cover).
     const int r = 1, nz = d->nz_local;

@@ -97,6 +97,7 @@ struct DenseArgs
     int32_t wpr;          // summary words per row
     int32_t zm0;          // first memory plane of the view
     int32_t fold, skip;   // view planes >= fold are shifted by skip (BOUNDARY view: two slabs)
+    int32_t flagsAlways;  // direct kernel: fetch the flag words with the populations instead of consulting the row summary first
     double  omega;
 };
 
@@ -128,6 +129,84 @@ struct Vec<double, 2>
 {
     using type = double2;
 };
+
+// Predicated, branch-free, non-coherent global loads, written as volatile inline PTX on purpose: the compiler keeps
+// volatile asm statements in program order and cannot wrap them in branches, so a kernel that lists all its loads first
+// really has all of them in flight before the first use (ncu showed ptxas otherwise interleaving the loads with the
+// shuffles that consume them: one exposed DRAM round trip per population).  pred == false yields zeros.
+__device__ __forceinline__ void ldPred(const float* p, bool pred, float (&v)[4])
+{
+    asm volatile(
+        "{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n}\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+        : "l"(p), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void ldPred(const float* p, bool pred, float (&v)[2])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\n"
+                 "@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n}\n"
+                 : "=f"(v[0]), "=f"(v[1])
+                 : "l"(p), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void ldPred(const float* p, bool pred, float (&v)[1])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f32 %0, 0f00000000;\n@q ld.global.nc.f32 %0, [%1];\n}\n"
+                 : "=f"(v[0])
+                 : "l"(p), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void ldPred(const double* p, bool pred, double (&v)[2])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f64 %0, 0d0000000000000000;\nmov.f64 %1, 0d0000000000000000;\n"
+                 "@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n}\n"
+                 : "=d"(v[0]), "=d"(v[1])
+                 : "l"(p), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ void ldPred(const double* p, bool pred, double (&v)[1])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.nc.f64 %0, [%1];\n}\n"
+                 : "=d"(v[0])
+                 : "l"(p), "r"((uint32_t)pred));
+}
+__device__ __forceinline__ float ldPred1(const float* p, bool pred)
+{
+    float v[1];
+    ldPred(p, pred, v);
+    return v[0];
+}
+__device__ __forceinline__ double ldPred1(const double* p, bool pred)
+{
+    double v[1];
+    ldPred(p, pred, v);
+    return v[0];
+}
+// coherent variants (the output field: cells this kernel never writes, but next to cells it does)
+__device__ __forceinline__ float ldPredCoherent1(const float* p, bool pred, float keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f32 %0, [%1];\n}\n" : "+f"(keep) : "l"(p), "r"((uint32_t)pred));
+    return keep;
+}
+__device__ __forceinline__ double ldPredCoherent1(const double* p, bool pred, double keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
+    return keep;
+}
+template <int VEC>
+__device__ __forceinline__ void ldFlags(const uint32_t* p, uint32_t (&v)[VEC])
+{
+    if constexpr (VEC == 4)
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
+    else if constexpr (VEC == 2)
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];\n" : "=r"(v[0]), "=r"(v[1]) : "l"(p));
+    else
+        asm volatile("ld.global.nc.u32 %0, [%1];\n" : "=r"(v[0]) : "l"(p));
+}
+__device__ __forceinline__ uint2 ldPredU2(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 
 template <typename T, int VEC>
 __device__ __forceinline__ void ldVec(const T* __restrict__ p, T (&v)[VEC])

@@ -204,87 +204,180 @@ struct CollideD3Q27Fast
 
 // =============================================================== streaming
 // Population q of cell x is pulled from cell x - c_q (LbmTools.h:78-96 / stream.h:28-43).
+//
+// Two phases so that EVERY global load of a thread is in flight before the first one is consumed: loadOne issues the
+// aligned 16-byte row load (and, on the two edge lanes of populations with c_x != 0, the one scalar the warp shuffle
+// cannot supply); shiftOne then realises the x shift in registers.
 template <class L, int q, typename T, int VEC>
-__device__ __forceinline__ void pullOne(const T* __restrict__ cell0, const DenseArgs& a, const int x0, const int y,
-                                        const int zm, const int lane, T (&f)[VEC])
+__device__ __forceinline__ void loadOne(const T* __restrict__ cell0, const DenseArgs& a, const int x0, const int y, const int zm,
+                                        const int lane, T (&v)[VEC], T& edge)
 {
     constexpr int cx = L::c(q, 0), cy = L::c(q, 1), cz = L::c(q, 2);
     const int     ys = y - cy, zs = zm - cz;
     // warp-uniform: rows outside the allocation are never dereferenced (an enclosed geometry has no bulk cell there)
     const bool ok = (cy == 0 || (unsigned)ys < (unsigned)a.ny) && (cz == 0 || (unsigned)zs < (unsigned)a.nzm);
     const T*   p = cell0 + (q * a.pitch_q - cz * a.pitch_z - (int64_t)cy * a.pitch_y);
-    T          v[VEC];
-    if (ok) {
-        ldVec<T, VEC>(p, v);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            v[i] = T(0);
-    }
-    if constexpr (cx == 0) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            f[i] = v[i];
-    } else if constexpr (cx == 1) {
+    ldPred(p, ok, v);
+    edge = T(0);
+    if constexpr (cx == 1)
+        edge = ldPred1(p - 1, lane == 0 && ok && x0 > 0);
+    else if constexpr (cx == -1)
+        edge = ldPred1(p + VEC, lane == 31 && ok && x0 + VEC < a.pitch_y);
+}
+
+template <class L, int q, typename T, int VEC>
+__device__ __forceinline__ void shiftOne(const int lane, T (&v)[VEC], const T edge)
+{
+    constexpr int cx = L::c(q, 0);
+    if constexpr (cx == 1) {
         T e = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
         if (lane == 0)
-            e = (ok && x0 > 0) ? __ldg(p - 1) : T(0);
-        f[0] = e;
+            e = edge;
 #pragma unroll
-        for (int i = 1; i < VEC; ++i)
-            f[i] = v[i - 1];
-    } else {
+        for (int i = VEC - 1; i > 0; --i)
+            v[i] = v[i - 1];
+        v[0] = e;
+    } else if constexpr (cx == -1) {
         T e = __shfl_down_sync(0xffffffffu, v[0], 1);
         if (lane == 31)
-            e = (ok && x0 + VEC < a.pitch_y) ? __ldg(p + VEC) : T(0);
-        f[VEC - 1] = e;
+            e = edge;
 #pragma unroll
         for (int i = 0; i < VEC - 1; ++i)
-            f[i] = v[i + 1];
+            v[i] = v[i + 1];
+        v[VEC - 1] = e;
     }
 }
 
-// Wall fix-up of population q for one cell: bit q of the mask set <=> the cell at x - c_q is not bulk; then
+template <class L, typename T, int VEC, int... Qs>
+__device__ __forceinline__ void loadAll(std::integer_sequence<int, Qs...>, const T* __restrict__ cell0, const DenseArgs& a,
+                                        const int x0, const int y, const int zm, const int lane, T (&f)[L::Q][VEC], T (&edge)[L::Q])
+{
+    (loadOne<L, Qs, T, VEC>(cell0, a, x0, y, zm, lane, f[Qs], edge[Qs]), ...);
+}
+template <class L, typename T, int VEC, int... Qs>
+__device__ __forceinline__ void shiftAll(std::integer_sequence<int, Qs...>, const int lane, T (&f)[L::Q][VEC], const T (&edge)[L::Q])
+{
+    (shiftOne<L, Qs, T, VEC>(lane, f[Qs], edge[Qs]), ...);
+}
+
+// ---------------------------------------------------------------- wall fix-up (half-way bounce-back, moving walls)
+// Bit q of the cell's mask set <=> the cell at x - c_q is not bulk; then
 //   in[q] = f_opp(q)(x) + f_opp(q)(x - c_q)      (LbmTools.h:78-96; stream.h:36-41)
-template <class L, int q, typename T>
-__device__ __forceinline__ void fixOne(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, T& fq)
+// Both operands live outside the data the streaming step fetched, so they cost a round trip to memory.  All loads of
+// one cell are issued together (a cell between two walls aside: q and opp(q) share a slot, the second is fetched late).
+template <class L>
+struct Pairs
 {
-    if constexpr (q != L::REST) {
-        if (m & (1u << q)) {
-            constexpr int o = L::opp(q);
-            const T*      po = cell + o * a.pitch_q;
-            const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
-            fq = __ldg(po) + __ldg(po - dn);
+    // pair p = (lo, hi = opp(lo)), lo < hi, REST excluded: D3Q19 -> 9 pairs (g, g+10), D3Q27 -> 13 pairs
+    static constexpr int N = (L::Q - 1) / 2;
+    __host__ __device__ static constexpr int lo(int p)
+    {
+        int n = 0;
+        for (int q = 0; q < L::Q; ++q) {
+            if (q != L::REST && q < L::opp(q)) {
+                if (n == p)
+                    return q;
+                ++n;
+            }
         }
+        return -1;
+    }
+};
+
+template <class L, typename T, int VEC, int P>
+__device__ __forceinline__ void fixLoad(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i,
+                                        T (&f)[L::Q][VEC], T& tb)
+{
+    constexpr int q = Pairs<L>::lo(P), o = L::opp(q);
+    const bool    bq = (m >> q) & 1u, bo = (m >> o) & 1u;
+    tb = T(0);
+    if (bq | bo) {
+        // bq: f_o(x) + f_o(x - c_q);   bo (only): f_q(x) + f_q(x - c_o) = f_q(x) + f_q(x + c_q)
+        // the first operand lands in the slot it replaces (what was pulled from the wall cell is never used)
+        const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
+        const T*      src = cell + (bq ? o : q) * a.pitch_q;
+        const T       first = __ldg(src);
+        tb = __ldg(bq ? src - dn : src + dn);
+        if (bq)
+            f[q][i] = first;
+        else
+            f[o][i] = first;
+    }
+}
+template <class L, typename T, int VEC, int P>
+__device__ __forceinline__ void fixUse(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i, const T tb,
+                                       T (&f)[L::Q][VEC])
+{
+    constexpr int q = Pairs<L>::lo(P), o = L::opp(q);
+    const bool    bq = (m >> q) & 1u, bo = (m >> o) & 1u;
+    if (bq)
+        f[q][i] = f[q][i] + tb;
+    else if (bo)
+        f[o][i] = f[o][i] + tb;
+    if (bq && bo) {  // walls on both sides of the cell along c_q: the second one is fetched late
+        const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
+        const T*      src = cell + q * a.pitch_q;
+        f[o][i] = __ldg(src) + __ldg(src + dn);
     }
 }
 
-template <class L, typename T, int VEC, int... Qs>
-__device__ __forceinline__ void pullAll(std::integer_sequence<int, Qs...>, const T* __restrict__ cell0, const DenseArgs& a,
-                                        const int x0, const int y, const int zm, const int lane, T (&f)[L::Q][VEC])
+template <class L, typename T, int VEC, int P0, int P1, int... Ps>
+__device__ __forceinline__ void fixChunk(std::integer_sequence<int, Ps...>, const T* __restrict__ cell, const DenseArgs& a,
+                                         const uint32_t m, const int i, T (&f)[L::Q][VEC])
 {
-    (pullOne<L, Qs, T, VEC>(cell0, a, x0, y, zm, lane, f[Qs]), ...);
+    constexpr int N = P1 - P0;
+    T             tb[N];
+    (fixLoad<L, T, VEC, P0 + Ps>(cell, a, m, i, f, tb[Ps]), ...);      // pass 1: every load of the chunk
+    (fixUse<L, T, VEC, P0 + Ps>(cell, a, m, i, tb[Ps], f), ...);       // pass 2: use them
 }
-template <class L, typename T, int VEC, int... Qs>
-__device__ __forceinline__ void fixAll(std::integer_sequence<int, Qs...>, const T* __restrict__ cell, const DenseArgs& a,
-                                       const uint32_t m, const int i, T (&f)[L::Q][VEC])
+
+// CH = pairs per batch: CH temporaries live next to the Q*VEC values
+template <class L, typename T, int VEC, int CH>
+__device__ __forceinline__ void fixCell(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i,
+                                        T (&f)[L::Q][VEC])
 {
-    (fixOne<L, Qs, T>(cell, a, m, f[Qs][i]), ...);
+    constexpr int NP = Pairs<L>::N;
+    if constexpr (NP > 0 * CH)
+        fixChunk<L, T, VEC, 0, (NP < CH ? NP : CH)>(std::make_integer_sequence<int, (NP < CH ? NP : CH)>{}, cell, a, m, i, f);
+    if constexpr (NP > 1 * CH)
+        fixChunk<L, T, VEC, CH, (NP < 2 * CH ? NP : 2 * CH)>(std::make_integer_sequence<int, (NP < 2 * CH ? NP : 2 * CH) - CH>{}, cell,
+                                                             a, m, i, f);
+    if constexpr (NP > 2 * CH)
+        fixChunk<L, T, VEC, 2 * CH, NP>(std::make_integer_sequence<int, NP - 2 * CH>{}, cell, a, m, i, f);
+    static_assert(NP <= 3 * CH, "chunking covers three batches");
 }
 
 // Wall fix-ups, collision and stores of the VEC cells one thread owns (shared by the direct and the TMA kernel).
-template <class COL, typename T, int VEC>
+template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5)>
 __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
                                             const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC])
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
+    bool allBulk = true, anyBulk = false;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        allBulk = allBulk && flagIsBulk(fl[i]);
+        anyBulk = anyBulk || flagIsBulk(fl[i]);
+    }
     if (special) {
+        // Non-bulk cells are never updated (LbmTools.h:304).  A thread that owns bulk AND non-bulk cells still leaves
+        // through one 16-byte store per population: the non-bulk cells carry the value the output field already holds,
+        // fetched here — together with the wall fix-up operands, one round trip for both — into the slots whose pulled
+        // values are never used, and kept through the collision by a select.  Nobody else writes those cells.
+        const bool mixed = anyBulk && !allBulk;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const bool keepOld = mixed && !flagIsBulk(fl[i]);
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                f[q][i] = ldPredCoherent1(out0 + q * a.pitch_q + i, keepOld, f[q][i]);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const uint32_t m = fl[i] & kMaskBits;
             if (m != 0 && flagIsBulk(fl[i]))
-                fixAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0 + i, a, m, i, f);
+                fixCell<L, T, VEC, CH>(cell0 + i, a, m, i, f);
         }
     }
 
@@ -296,35 +389,23 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
         for (int q = 0; q < Q; ++q)
             p[q] = f[q][i];
         COL::run(p, omega);
+        const bool bulk = flagIsBulk(fl[i]);
 #pragma unroll
         for (int q = 0; q < Q; ++q)
-            f[q][i] = p[q];
+            f[q][i] = bulk ? p[q] : f[q][i];
     }
 
-    bool allBulk = true;
+    if (!anyBulk)
+        return;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i)
-        allBulk = allBulk && flagIsBulk(fl[i]);
-    if (allBulk) {  // the common case, also for wall-adjacent cells: full 16-byte stores
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            if (flagIsBulk(fl[i])) {
-#pragma unroll
-                for (int q = 0; q < Q; ++q)
-                    __stcs(out0 + q * a.pitch_q + i, f[q][i]);
-            }
-        }
-    }
+    for (int q = 0; q < Q; ++q)
+        stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);
 }
 
 // =============================================================== the kernel
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
 template <class COL, typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads) k_dense_step(const DenseArgs a)
+__global__ void __launch_bounds__(kStepThreads, (VEC * sizeof(T) * COL::Q > 200 ? 2 : 3)) k_dense_step(const DenseArgs a)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -336,36 +417,50 @@ __global__ void __launch_bounds__(kStepThreads) k_dense_step(const DenseArgs a)
     const int xw = seg * (32 * VEC);
     if (xw >= a.nx || y >= a.ny)
         return;  // warp-uniform
-    const int64_t  row = (int64_t)zm * a.ny + y;
-    const int      chunk0 = seg * VEC;  // the warp's VEC chunks lie in one summary word (VEC divides 32)
-    const uint2    s = __ldg(a.summary + row * a.wpr + (chunk0 >> 5));
-    const uint32_t cm = (1u << VEC) - 1u;
-    const uint32_t wbulk = (s.y >> (chunk0 & 31)) & cm;
-    if (wbulk == 0)
-        return;  // no bulk cell in this warp's segment: nothing to update
-    const uint32_t wspec = (s.x >> (chunk0 & 31)) & cm;
-    const int      x0 = xw + lane * VEC;
-    const bool     special = (wspec >> ((lane * VEC) >> 5)) & 1u;
-
+    const int64_t row = (int64_t)zm * a.ny + y;
+    const int     chunk0 = seg * VEC;  // the warp's VEC chunks lie in one summary word (VEC divides 32)
+    const int     x0 = xw + lane * VEC;
     const int64_t cellOff = (int64_t)zm * a.pitch_z + (int64_t)y * a.pitch_y + x0;
     const T*      cell0 = reinterpret_cast<const T*>(a.in) + cellOff;
 
+    // every load of the thread goes out before anything is consumed
+    uint2    s = make_uint2(0u, 0u);
     uint32_t fl[VEC];
-    if (special) {
-        using FV = typename Vec<float, VEC>::type;  // same width as VEC uint32
-        const FV  t = __ldg(reinterpret_cast<const FV*>(a.flags + cellOff));
-        const uint32_t* e = reinterpret_cast<const uint32_t*>(&t);
+    if (a.flagsAlways)
+        ldFlags<VEC>(a.flags + cellOff, fl);
+    else
+        s = ldPredU2(a.summary + row * a.wpr + (chunk0 >> 5));
+    T f[Q][VEC], edge[Q];
+    loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, lane, f, edge);
+
+    bool special;
+    if (a.flagsAlways) {
+        bool plain = true, bulk = false;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            fl[i] = e[i];
+        for (int i = 0; i < VEC; ++i) {
+            plain = plain && fl[i] == kPlainBulk;
+            bulk = bulk || flagIsBulk(fl[i]);
+        }
+        if (!__any_sync(0xffffffffu, bulk))
+            return;  // no bulk cell in this warp's segment: nothing to update
+        special = !plain;
     } else {
+        const uint32_t cm = (1u << VEC) - 1u;
+        const uint32_t wbulk = (s.y >> (chunk0 & 31)) & cm;
+        if (wbulk == 0)
+            return;  // no bulk cell in this warp's segment: nothing to update
+        const uint32_t wspec = (s.x >> (chunk0 & 31)) & cm;
+        special = (wspec >> ((lane * VEC) >> 5)) & 1u;
+        if (special) {
+            ldFlags<VEC>(a.flags + cellOff, fl);
+        } else {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            fl[i] = kPlainBulk;
+            for (int i = 0; i < VEC; ++i)
+                fl[i] = kPlainBulk;
+        }
     }
 
-    T f[Q][VEC];
-    pullAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, lane, f);
+    shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, lane, f, edge);
 
     finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
 }
@@ -375,10 +470,10 @@ template <class COL, typename T, int VEC>
 inline cudaError_t launchStepVec(const DenseArgs& a, int nzView, int rowsLog2, cudaStream_t st)
 {
     const int segs = (a.nx + 32 * VEC - 1) / (32 * VEC);
-    int       warps = kStepThreads / 32;
-    int       sx = 1;
-    while (sx * 2 <= warps && sx < segs)
-        sx *= 2;
+    // default: the 8 warps of a block take the same x segment of 8 consecutive rows, so that the warps which need the
+    // extra round trip of wall handling (segments touching a wall) share blocks and do not hold back plain ones
+    int warps = kStepThreads / 32;
+    int sx = 1;
     int rows = warps / sx;
     if (rowsLog2 > 0) {
         rows = 1 << (rowsLog2 - 1);

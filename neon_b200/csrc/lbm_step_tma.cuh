@@ -56,6 +56,7 @@ struct TmaCfg
     static constexpr int MAX_TX = 128;       // box width TX + CPT must stay <= 256
     static constexpr int THREADS = 32 + MAX_GROUPS * GROUP_THREADS;
     static constexpr int MAX_ROWS = 16;
+    static constexpr int FIX_CHUNK = 5;  // wall fix-up loads per batch (register budget)
     static_assert(MAX_STAGES * (16 + MAX_ROWS * 4 + 4) <= TAIL_BYTES, "tail too small");
     __host__ __device__ static constexpr int shiftedBefore(int q)
     {
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(TmaCfg<COL, T>::THREADS, 1)
             if (!hasBulk)
                 continue;
             const int64_t cellOff = (int64_t)zm * a.pitch_z + (int64_t)y * a.pitch_y + x;
-            finishCells<COL, T, CPT>(a, reinterpret_cast<const T*>(a.in) + cellOff, reinterpret_cast<T*>(a.out) + cellOff, fl,
+            finishCells<COL, T, CPT, Cfg::FIX_CHUNK>(a, reinterpret_cast<const T*>(a.in) + cellOff, reinterpret_cast<T*>(a.out) + cellOff, fl,
                                      special, f);
         }
     }

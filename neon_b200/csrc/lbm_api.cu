@@ -150,7 +150,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.pitch_q = d->pitch_q;
     a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
     a.omega = omega;
-    a.flagsAlways = (opts >> 20) & 1;
+    a.flagsAlways = ((opts >> 20) & 1) ? 0 : 1;
     // Views split at stencil radius 1 (both lattices): INTERNAL = local z in [1, nz-1), BOUNDARY = {0, nz-1}
     // (the reference's BOUNDARY span folds wrongly; this is the intended cover).
     const int r = 1, nz = d->nz_local;
@@ -183,7 +183,9 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     const int   q = (kind == nlbm::kD3Q27_F32 || kind == nlbm::kD3Q27_F64) ? 27 : 19;
     CUtensorMap tmapA, tmapB, tmapF;
     const int   promo = (opts >> 16) & 0x3;
-    if (kernelSel == 0 || kernelSel == 2) {
+    // auto = the direct kernel: since all its loads are issued up front it beats the TMA-fed variant on every measured
+    // configuration (profiles/); the TMA kernel stays selectable
+    if (kernelSel == 2) {
         int tx, ty;
         nlbm::tmaTileShape(elemBytes, d->nx, &tx, &ty);
         const int sms = smCount();
@@ -196,7 +198,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
         } else if (kernelSel == 2) {
             return fail(NLBM_ERR_CUDA, "cannot build the TMA descriptor (cuTensorMapEncodeTiled unavailable or refused)");
         }
-    } else if (kernelSel != 1) {
+    } else if (kernelSel != 0 && kernelSel != 1) {
         return fail(NLBM_ERR_INVALID, "bad kernel selector %d", kernelSel);
     }
     cudaStream_t st = (cudaStream_t)stream;

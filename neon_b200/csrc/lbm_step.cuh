@@ -403,9 +403,13 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
 }
 
 // =============================================================== the kernel
+// Resident blocks per SM asked of ptxas, from the registers the Q x VEC population values of a thread occupy: the kernel is
+// latency-bound on its one round trip to HBM, so it wants as many warps as it can have without spilling those values.
+__host__ __device__ constexpr int stepMinBlocks(int valueRegs) { return valueRegs <= 40 ? 3 : (valueRegs <= 80 ? 2 : 1); }
+
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
 template <class COL, typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads, (VEC * sizeof(T) * COL::Q > 200 ? 2 : 3)) k_dense_step(const DenseArgs a)
+__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -493,8 +497,12 @@ template <class COL, typename T>
 inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st)
 {
     constexpr int maxVec = 16 / (int)sizeof(T);
-    if (vec <= 0 || vec > maxVec)
+    if (vec <= 0 || vec > maxVec) {
+        // default: the widest access whose values fit two resident blocks per SM (D3Q19: 16 bytes, D3Q27: 8 bytes)
         vec = maxVec;
+        while (vec > 1 && COL::Q * vec * (int)sizeof(T) / 4 > 80)
+            vec >>= 1;
+    }
     while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
         vec >>= 1;
     if constexpr (maxVec >= 4) {

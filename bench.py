@@ -259,8 +259,9 @@ def main():
     # launches of OUR kernels per step on this rank: the step kernel per view (+ pack/unpack per neighbour)
     dn, up = grid.neighbours()
     nnb = (dn is not None) + (up is not None)
-    launches_step = 1 if world == 1 else ((2 if occ != nb.Occ.none else 1) + (2 * nnb if args.transport in ("auto", "packed") else
-                                                                                (nnb if args.transport == "ipc" else 0)))
+    # halo per neighbour: ipc = push + signal + wait kernels, packed = pack + unpack kernels (+ NCCL's own), views = NCCL only
+    per_nb = {"auto": 3, "ipc": 3, "packed": 2, "views": 0}[args.transport]
+    launches_step = 1 if world == 1 else ((2 if occ != nb.Occ.none else 1) + per_nb * nnb)
 
     # --- roofline of the dominant kernel (k_dense_step): algorithmic bytes / measured launch duration ------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -180,6 +180,25 @@ int nlbm_dense_halo_pack(const nlbm_dense_desc* d, const void* field, int elem_b
 int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
                            const void* buffer, void* stream);
 
+/* Device-side ordering for the peer-store halo transport between PROCESSES (one per GPU): the reference orders its
+ * cudaMemcpyPeerAsync copies with events of one process plus host-blocking syncs (SynchronizationContainer.h:37-42);
+ * across processes a counter word in the receiver's memory replaces the event.
+ *   nlbm_flag_signal: enqueue "*flag = value" after everything already in `stream` (system-wide visibility);
+ *                     `flag` may be a CUDA-IPC / peer mapping of memory on the neighbouring GPU.
+ *   nlbm_flag_wait  : enqueue a wait until *flag >= value (wrap-safe) or until timeout_ms elapsed, in which case
+ *                     *d_err (device int32, may be NULL) is incremented and the stream continues.                   */
+/* CUDA-IPC plumbing for the peer-store transport between processes.  export: handle of the ALLOCATION that contains `ptr`
+ * and ptr's byte offset inside it; import (in another process, with ITS device current): maps that allocation and returns
+ * its base — peer access to the exporting device is enabled on demand.  A handle must be imported once per process.       */
+int nlbm_ipc_export(const void* ptr, unsigned char* handle64, uint64_t* offset);
+int nlbm_ipc_import(const unsigned char* handle64, void** base);
+int nlbm_ipc_close(void* base);
+/* Enables direct access from the current device to `peer_device` (the reference does this for every device pair when
+ * the Backend is built, libNeonSet/src/set/DevSet.cpp:80-100).  Idempotent.                                          */
+int nlbm_enable_peer_access(int peer_device);
+int nlbm_flag_signal(uint32_t* flag, uint32_t value, void* stream);
+int nlbm_flag_wait(const uint32_t* flag, uint32_t value, uint32_t timeout_ms, int32_t* d_err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

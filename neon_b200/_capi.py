@@ -95,6 +95,12 @@ _SIGNATURES = {
     "nlbm_dense_halo_push": (C.c_int, [_D, _P, _D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "nlbm_dense_halo_pack": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_size_t), _P]),
     "nlbm_dense_halo_unpack": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "nlbm_ipc_export": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
+    "nlbm_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "nlbm_ipc_close": (C.c_int, [_P]),
+    "nlbm_enable_peer_access": (C.c_int, [C.c_int]),
+    "nlbm_flag_signal": (C.c_int, [_P, C.c_uint32, _P]),
+    "nlbm_flag_wait": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
 }
 
 _lib = None

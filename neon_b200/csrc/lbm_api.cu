@@ -437,4 +437,87 @@ int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes
     return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo unpack launch");
 }
 
+int nlbm_ipc_export(const void* ptr, unsigned char* handle64, uint64_t* offset)
+{
+    if (!ptr || !handle64 || !offset)
+        return fail(NLBM_ERR_INVALID, "null argument");
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range = nullptr;
+    if (!range) {
+        void*                           p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return fail(NLBM_ERR_CUDA, "cuMemGetAddressRange unavailable");
+        range = (RangeFn)p;
+    }
+    CUdeviceptr base = 0;
+    size_t      size = 0;
+    if (range(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS)
+        return fail(NLBM_ERR_CUDA, "cuMemGetAddressRange failed: not a device allocation");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t        e = cudaIpcGetMemHandle(&h, (void*)base);
+    if (e != cudaSuccess)
+        return cudaFail(e, "cudaIpcGetMemHandle");
+    memcpy(handle64, &h, 64);
+    *offset = (uint64_t)((CUdeviceptr)ptr - base);
+    return NLBM_OK;
+}
+
+int nlbm_ipc_import(const unsigned char* handle64, void** base)
+{
+    if (!handle64 || !base)
+        return fail(NLBM_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "cudaIpcOpenMemHandle");
+}
+
+int nlbm_ipc_close(void* base)
+{
+    cudaError_t e = cudaIpcCloseMemHandle(base);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "cudaIpcCloseMemHandle");
+}
+
+int nlbm_enable_peer_access(int peer_device)
+{
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return cudaFail(e, "cudaGetDevice");
+    if (peer_device == dev)
+        return NLBM_OK;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+    if (e != cudaSuccess)
+        return cudaFail(e, "cudaDeviceCanAccessPeer");
+    if (!can)
+        return fail(NLBM_ERR_UNSUPPORTED, "device %d cannot access device %d directly", dev, peer_device);
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();  // clear the sticky-less error state
+        return NLBM_OK;
+    }
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "cudaDeviceEnablePeerAccess");
+}
+
+int nlbm_flag_signal(uint32_t* flag, uint32_t value, void* stream)
+{
+    if (!flag || ((uintptr_t)flag & 3))
+        return fail(NLBM_ERR_INVALID, "flag pointer null or misaligned");
+    cudaError_t e = nlbm::launchFlagSignal(flag, value, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag signal launch");
+}
+
+int nlbm_flag_wait(const uint32_t* flag, uint32_t value, uint32_t timeout_ms, int32_t* d_err, void* stream)
+{
+    if (!flag || ((uintptr_t)flag & 3))
+        return fail(NLBM_ERR_INVALID, "flag pointer null or misaligned");
+    if (timeout_ms == 0)
+        return fail(NLBM_ERR_INVALID, "a wait needs a time-out");
+    cudaError_t e = nlbm::launchFlagWait(flag, value, timeout_ms, d_err, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag wait launch");
+}
+
 }  // extern "C"

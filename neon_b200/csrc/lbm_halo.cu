@@ -37,4 +37,44 @@ cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, siz
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- device-side ordering between GPUs
+// One process per GPU cannot order a neighbour's stream with CUDA events without a host hand-shake per iteration.  The
+// peer-store halo transport therefore orders with flag words: after its face copy (stream order) the sender publishes a
+// counter in the receiver's memory, and the receiver's stream holds a one-thread kernel that waits for it.  The wait
+// gives up after timeoutMs (and records it) so that a lost neighbour cannot hang the GPU.
+__global__ void k_flag_signal(volatile uint32_t* flag, uint32_t value)
+{
+    __threadfence_system();  // the face copy of the previous kernel in this stream is visible system-wide first
+    *flag = value;
+    __threadfence_system();
+}
+
+__global__ void k_flag_wait(const volatile uint32_t* flag, uint32_t value, unsigned long long timeoutNs, int32_t* err)
+{
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*flag - value) < 0) {  // counters only grow; the signed difference tolerates wrap-around
+        __nanosleep(200);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) {
+            if (err)
+                atomicAdd(err, 1);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t st)
+{
+    k_flag_signal<<<1, 1, 0, st>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launchFlagWait(const uint32_t* flag, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st)
+{
+    k_flag_wait<<<1, 1, 0, st>>>(flag, value, (unsigned long long)timeoutMs * 1000000ull, err);
+    return cudaGetLastError();
+}
+
 }  // namespace nlbm

@@ -43,6 +43,8 @@ struct PlaneList
     int64_t src[27];  // byte offsets
     int64_t dst[27];
 };
+cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t st);
+cudaError_t launchFlagWait(const uint32_t* flag, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st);
 cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, size_t planeBytes, cudaStream_t st);
 
 }  // namespace nlbm

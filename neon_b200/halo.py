@@ -36,7 +36,10 @@ class HaloUpdateContainer(Container):
         self.lattice_q = lattice_q if semantic == StencilSemantic.streaming else 0
         bk = field.grid.backend
         if transport == "auto":
-            transport = "packed" if bk.runtime == Runtime.stream else "views"
+            # CUDA: peer stores through CUDA-IPC mappings (one node, NVLink/NVSwitch: every bench/test topology here);
+            # set NEON_B200_HALO=packed|views to route the faces through NCCL instead
+            import os
+            transport = os.environ.get("NEON_B200_HALO", "ipc") if bk.runtime == Runtime.stream else "views"
         if transport not in ("packed", "views", "ipc"):
             raise ValueError(transport)
         if transport != "views" and bk.runtime != Runtime.stream:
@@ -121,6 +124,10 @@ class HaloUpdateContainer(Container):
             capi.call("nlbm_dense_halo_unpack", C.byref(d), f.data.data_ptr(), *args, -1, self._buf("r_up", -1).data_ptr(), st)
         if dn is not None:
             capi.call("nlbm_dense_halo_unpack", C.byref(d), f.data.data_ptr(), *args, +1, self._buf("r_dn", +1).data_ptr(), st)
+
+    def timeouts(self) -> int:
+        """Waits of the peer-store transport that gave up (a neighbour never signalled); 0 for the other transports."""
+        return 0 if self._ipc is None else self._ipc.timeouts()
 
     def _run_ipc(self, streamIdx: int) -> None:
         from .ipc import IpcHalo

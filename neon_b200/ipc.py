@@ -1,0 +1,114 @@
+"""Peer-store halo transport between processes: CUDA-IPC mappings + device-side flags.
+
+The reference drives every GPU from one process, so a halo update is a ``cudaMemcpyPeerAsync`` between two of its own
+allocations (libNeonSet/src/set/DevSet.cpp:401-437) ordered by its own events and host-blocking syncs.  Here every GPU
+belongs to its own process.  Once, at first use, each rank exports its field (and a few flag words) through CUDA IPC to
+its z-neighbours; afterwards a halo update is, per neighbour,
+
+    nlbm_dense_halo_push   my boundary plane (crossing populations only) -> the neighbour's ghost plane, over NVLink
+    nlbm_flag_signal       publish my update counter in the neighbour's flag word (after the copy, stream order)
+    nlbm_flag_wait         hold my stream until the neighbour's counter for this update arrived
+
+all enqueued on the stream the Skeleton gave the halo node — no host synchronisation, no staging buffer, no NCCL call on
+the data path.  Hazards: RAW — the ghost plane is complete before my BOUNDARY kernel because that
+kernel follows the wait in stream order; WAR — a neighbour overwrites my ghost plane of field A for update k+1 only
+after its own BOUNDARY kernel of the iteration in between, which waited for my signal of that iteration, which I enqueue
+after the BOUNDARY kernel that read the plane.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi as capi
+
+_FLAG_WORDS = 32
+FROM_BELOW, FROM_ABOVE = 0, 16  # flag word written by the rank below / above (different 64-byte lines)
+TIMEOUT_MS = 20000
+
+_imported = {}  # handle bytes -> base address of the mapping in this process (a handle may be opened once per process)
+
+
+def export_ptr(ptr: int):
+    """(handle bytes, offset) of the device allocation that contains ``ptr`` — picklable."""
+    h = C.create_string_buffer(64)
+    off = C.c_uint64()
+    capi.call("nlbm_ipc_export", C.c_void_p(ptr), h, C.byref(off))
+    return bytes(h.raw), int(off.value)
+
+
+def import_ptr(handle: bytes, offset: int) -> int:
+    """Address, in this process, of what ``export_ptr`` described in another one (same node)."""
+    if handle not in _imported:
+        base = C.c_void_p()
+        capi.call("nlbm_ipc_import", C.create_string_buffer(handle, 64), C.byref(base))
+        _imported[handle] = int(base.value)
+    return _imported[handle] + offset
+
+
+class IpcHalo:
+    def __init__(self, halo):
+        self.halo = halo
+        f = halo.field
+        g = f.grid
+        bk = g.backend
+        self.count = 0
+        self.flags = torch.zeros(_FLAG_WORDS, dtype=torch.int32, device=bk.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=bk.device)
+        torch.cuda.synchronize(bk.device)
+        # every rank publishes (field, flags) handles; each maps only its neighbours' allocations
+        mine = (export_ptr(f.data.data_ptr()), export_ptr(self.flags.data_ptr()))
+        handles = [None] * bk.world
+        dist.all_gather_object(handles, mine, group=bk.group)
+        dn, up = g.neighbours()
+        self.peer = {}
+        for nbr in (dn, up):
+            if nbr is None:
+                continue
+            hf, hg = handles[nbr]
+            self.peer[nbr] = (import_ptr(*hf), import_ptr(*hg))  # addresses aliasing the neighbour's memory
+        self._descs = self._neighbour_descs()
+        bk.barrier()
+
+    def _neighbour_descs(self):
+        """Descriptor of each neighbour's partition (same box, its own slab height)."""
+        f = self.halo.field
+        g = f.grid
+        out = {}
+        for nbr in self.peer:
+            d = g.desc(f, None, None).clone()
+            d.nz_local = g.sizes[nbr]
+            d.z_origin = g.origins[nbr]
+            d.pitch_q = d.pitch_z * (d.nz_local + 2 * d.z_halo)
+            d.pop_in = None
+            out[nbr] = d
+        return out
+
+    def run(self, streamIdx: int) -> None:
+        h = self.halo
+        f = h.field
+        g = f.grid
+        bk = g.backend
+        st = bk.streamHandle(streamIdx)
+        mine = g.desc(f, None, None)
+        dn, up = g.neighbours()
+        self.count += 1
+        k = self.count
+        args = (f.elem_bytes, f.cardinality, h.lattice_q)
+        # push + signal
+        for nbr, direction, slot in ((up, +1, FROM_BELOW), (dn, -1, FROM_ABOVE)):
+            if nbr is None:
+                continue
+            pf, pg = self.peer[nbr]
+            capi.call("nlbm_dense_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(self._descs[nbr]), pf, *args, direction, st)
+            capi.call("nlbm_flag_signal", pg + 4 * slot, k, st)
+        # wait for what the neighbours pushed into my ghost planes
+        for nbr, slot in ((dn, FROM_BELOW), (up, FROM_ABOVE)):
+            if nbr is None:
+                continue
+            capi.call("nlbm_flag_wait", self.flags.data_ptr() + 4 * slot, k, TIMEOUT_MS, self.err.data_ptr(), st)
+
+    def timeouts(self) -> int:
+        return int(self.err.item())

@@ -84,6 +84,10 @@ class Skeleton:
         self._use_graph = bool(graph) and not multi and bk.runtime == Runtime.stream
         self._graph = None
 
+    def halos(self):
+        """The halo-update containers this sequence inserted."""
+        return [n.container for n in self.nodes if n.kind == "halo"]
+
     def schedule(self):
         """[(stream, kind, name, view)] in host issue order — what DB_multiGpuGraph.dot shows in the reference."""
         return [(n.stream, n.kind, n.name, n.view.name if n.view else None) for n in self.nodes]

@@ -1,9 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/pytest.log
-: > gpurun_out/bench_var.log
-for v in "" "--flags-summary-first" "--workload d3q27f64" "--workload d3q27f64 --vec 2" "--workload d3q27f64 --kernel tma" "--workload d3q27f64 --flags-summary-first" \
-   "--workload cavity64" "--workload cavity128" "--workload cavity256" "--arith reference" "--workload slab1024"; do
-  echo "== $v" >> gpurun_out/bench_var.log
-  timeout 120 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu $v 2>&1 | tail -3 >> gpurun_out/bench_var.log
-done
+timeout 600 python -m pytest tests/test_gpu_multiproc.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/pytest.log
+CUDA_LAUNCH_BLOCKING=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_debug.py ipc > gpurun_out/dbg_ipc.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 tests/mgpu_check.py > gpurun_out/mgpu2.log 2>&1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 50 --warmup 5 --transport ipc > gpurun_out/bench2_ipc.json 2> gpurun_out/bench2_ipc.err

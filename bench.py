@@ -74,6 +74,15 @@ def workload(args):
     if name == "d3q27f64":
         return dict(name=f"lid-driven cavity D3Q27 fp64 768x768x{96 * n} dGrid, z-slab over {n} GPU(s)", q=27, dtype="float64",
                     dim=(768, 768, 96 * n), scaling="weak")
+    if name == "sphere":
+        # BASELINE.json configs[3]: flow over a sphere on bGrid, 1024 x 512 x 512; integers recorded in SURVEY.md §8d
+        return dict(name=f"flow over sphere D3Q19 fp32 1024x512x512 bGrid (8^3 blocks, bounce-back), z block layers over {n} GPU(s)", q=19,
+                    dtype="float32", dim=(1024, 512, 512), scaling="strong", grid="bGrid", geom=2, sphere=(392.0, 277.0, 256.0, 60.0),
+                    omega=1.0 / (3.0 * 0.04 * 60.0 / 100.0 + 0.5))
+    if name.startswith("bcavity"):
+        e = int(name[len("bcavity"):])
+        return dict(name=f"lid-driven cavity D3Q19 fp32 {e}^3 bGrid (8^3 blocks)", q=19, dtype="float32", dim=(e, e, e),
+                    scaling="strong" if n > 1 else "weak", grid="bGrid")
     if name.startswith("cavity"):
         e = int(name[len("cavity"):])
         return dict(name=f"lid-driven cavity D3Q19 fp32 {e}^3 dGrid" + (f", z-slab over {n} GPUs" if n > 1 else ""), q=19,
@@ -217,15 +226,16 @@ def main():
     wl = workload(args)
     q, dtype, dim = wl["q"], np.dtype(wl["dtype"]), wl["dim"]
     cells = dim[0] * dim[1] * dim[2]
-    omega = nb.omega_from_re(dim[0])
+    omega = wl.get("omega", nb.omega_from_re(dim[0]))
     arith = nb.ARITH_FAST if args.arith == "fast" else nb.ARITH_REFERENCE
     opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[args.kernel]) \
         | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0)
     occ = nb.Occ.standard if args.occ == "standard" else nb.Occ.none
 
     bk = nb.Backend()
-    grid = nb.dGrid(bk, dim)
-    pop0, pop1, flag = P.setup_device(grid, q, dtype, P.CAVITY)
+    is_block = wl.get("grid", "dGrid") == "bGrid"
+    grid = nb.bGrid(bk, dim) if is_block else nb.dGrid(bk, dim)
+    pop0, pop1, flag = P.setup_device(grid, q, dtype, wl.get("geom", P.CAVITY), wl.get("sphere"))
     it = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q,
                          arith=arith, opts=opts, halo_transport=args.transport)
     main_stream = bk.stream(0)
@@ -270,7 +280,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_cell = 2 * q * dtype.itemsize
-    cells_rank = dim[0] * dim[1] * grid.nz_local
+    cells_rank = grid.n_blocks * 512 if is_block else dim[0] * dim[1] * grid.nz_local
     # per-launch duration of the step kernel, measured live: at N=1 the timed region holds exactly K launches of it
     kern_ms = None
     if world == 1:
@@ -291,17 +301,17 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            key = f"d3q{q}_{'f32' if dtype.itemsize == 4 else 'f64'}_{dim[0]}x{dim[1]}x{grid.nz_local}"
+            key = f"d3q{q}_{'f32' if dtype.itemsize == 4 else 'f64'}_{dim[0]}x{dim[1]}x{cells_rank // (dim[0] * dim[1])}" + ("_bgrid" if is_block else "")
             traffic = tj.get(key, {}).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_dense_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "k_block_step" if is_block else "k_dense_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "bytes_per_cell": bytes_cell, "cells_per_launch": cells_rank, "kernel_ms": kern_ms,
                 "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0}
 
     # --- e2e: host buffers -> device -> K iterations -> host ----------------------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not is_block:
         del it
         pop0.data = pop1.data = None
         torch.cuda.empty_cache()
@@ -351,7 +361,7 @@ def main():
                 "config": {"workload": wl["name"], "dim": list(dim), "lattice": f"D3Q{q}", "arith": args.arith, "kernel": args.kernel,
                            "occ": args.occ if world > 1 else "n/a (1 partition)", "halo_transport": args.transport if world > 1 else "n/a",
                            "l2": "inputs exceed L2 (two population fields of %.1f GB per GPU)" % (q * cells_rank * dtype.itemsize / 1e9),
-                           "partition": f"z-slabs of {grid.nz_local} planes" if world > 1 else "single partition"},
+                           "partition": (f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes") if world > 1 else "single partition"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_step * args.steps, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

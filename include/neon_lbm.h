@@ -180,6 +180,57 @@ int nlbm_dense_halo_pack(const nlbm_dense_desc* d, const void* field, int elem_b
 int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
                            const void* buffer, void* stream);
 
+
+/* ================================================================================================================
+ * Block-sparse (bGrid) partitions: 8 x 8 x 8-cell blocks (Neon::bGrid = StaticBlock<8,8,8>, libNeonDomain/include/Neon/
+ * domain/bGrid.h:5).  Replaces what the reference kernel receives by value: bSpan {firstDataBlockOffset, dataView}
+ * (bSpan.h:47-49) and bPartition members (bPartition.h:154-160: mem, cardinality, blockConnectivity, mask, origin).
+ *
+ * Memory layout (SoA per population; every block's tile of a population is one contiguous 2 KB-aligned run):
+ *   pop[q][blk][z][y][x]   element offset (q * n_blocks_alloc + blk) * 512 + z*64 + y*8 + x
+ *   flags[blk][z][y][x]    the dense flag word; cells that are not active carry class NLBM_UNDEFINED (this replaces the
+ *                          per-block active bit mask, StaticBlock.h:47-103)
+ *   info[blk][32]          words 0..26: neighbour block ids, index (dx+1) + 3*(dy+1) + 9*(dz+1) (bPartition_imp.h:194-198),
+ *                          NLBM_NO_BLOCK where there is none; words 27..29: global origin x, y, z of the block; 30..31 spare
+ * Block order inside a partition: [0, n_blocks) local blocks, sorted so that the blocks of the lowest block layer come
+ * first (n_down of them) and those of the highest layer last (n_up); [n_blocks, n_blocks_alloc) ghost blocks (copies of
+ * the facing layers of the z-neighbours: first the n_ghost_down blocks below, then those above).  (Reference:
+ * [blk][q][z][y][x] with 32-bit offsets — overflows beyond 2^32/19 cells per device, bPartition_imp.h:97-107.)          */
+#define NLBM_NO_BLOCK 0xFFFFFFFFu
+typedef struct nlbm_block_desc {
+    void*           pop_in;   /* device, borrowed */
+    void*           pop_out;  /* device, borrowed */
+    uint32_t*       flags;    /* device, borrowed */
+    const uint32_t* info;     /* device, borrowed */
+    uint32_t        n_blocks;        /* local blocks (the ones this partition updates) */
+    uint32_t        n_blocks_alloc;  /* local + ghost blocks */
+    uint32_t        n_down, n_up;    /* local blocks in the lowest / highest block layer (BOUNDARY view), 0 if unsplit */
+    int32_t         gnx, gny, gnz;   /* global box in cells */
+} nlbm_block_desc;
+
+/* Set-up on the device, as for dense partitions.  active_mask: 16 words per block (bit z*64+y*8+x, StaticBlock.h:47-103)
+ * or NULL = every in-domain cell of every block is active.  classify covers local and ghost blocks.                       */
+int nlbm_block_classify(const nlbm_block_desc* d, int geom, const double* sphere, const uint32_t* active_mask, void* stream);
+int nlbm_block_wall_mask(const nlbm_block_desc* d, int q, int32_t* d_bad, void* stream);
+int nlbm_block_init_pop_f32(const nlbm_block_desc* d, int q, double ulb, void* stream);
+int nlbm_block_init_pop_f64(const nlbm_block_desc* d, int q, double ulb, void* stream);
+
+/* THE HOT PATH on bGrid: LbmContainers::iteration (LbmTools.h:285-325) over the blocks of data_view
+ * (STANDARD: all local blocks; BOUNDARY: the n_down + n_up blocks of the outer layers; INTERNAL: the rest).              */
+int nlbm_d3q19_f32_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q19_f64_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q27_f32_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream);
+int nlbm_d3q27_f64_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream);
+
+/* Halo update of block-sparse partitions (bField::newHaloUpdate, bField_imp.h:173-332 — which ignores the cardinality and
+ * copies whole blocks; measured NaN upstream for Q = 19).  Here: for the populations that cross the face
+ * (lattice_q = 19 | 27; 0 = all ncomp components) only the facing z-slice (64 cells) of every boundary block moves.
+ *   dir = +1: z-slice 7 of src's n_up highest-layer blocks -> the same slice of dst's ghost-down blocks [dst_first_ghost ..)
+ *   dir = -1: z-slice 0 of src's n_down lowest-layer blocks -> the same slice of dst's ghost-up blocks
+ * The i-th boundary block of src corresponds to the i-th ghost block of dst (both sorted by block y, x).                   */
+int nlbm_block_halo_push(const nlbm_block_desc* src_desc, const void* src_field, const nlbm_block_desc* dst_desc, void* dst_field,
+                         uint32_t dst_first_ghost, int elem_bytes, int ncomp, int lattice_q, int dir, void* stream);
+
 /* Device-side ordering for the peer-store halo transport between PROCESSES (one per GPU): the reference orders its
  * cudaMemcpyPeerAsync copies with events of one process plus host-blocking syncs (SynchronizationContainer.h:37-42);
  * across processes a counter word in the receiver's memory replaces the event.

@@ -7,6 +7,7 @@ from ._capi import (ARITH_FAST, ARITH_REFERENCE, BOUNCE_BACK, BULK, KERNEL_AUTO,
                     NeonException, opt_kernel, opt_rows_log2,
                     opt_vec)
 from .backend import Backend, Runtime
+from .bgrid import bField, bFlagField, bGrid
 from .containers import Access, Container, Pattern, Token
 from .dgrid import DataView, FlagField, StencilSemantic, TransferMode, dField, dGrid, partition_z
 from .lbm import LbmContainers, LbmIteration, omega_from_re

@@ -66,10 +66,15 @@ class DenseDesc(C.Structure):
 class BlockDesc(C.Structure):
     """struct nlbm_block_desc"""
     _fields_ = [
-        ("pop_in", C.c_void_p), ("pop_out", C.c_void_p), ("flags", C.c_void_p),
-        ("connectivity", C.c_void_p), ("origin", C.c_void_p),
-        ("first_block", C.c_uint32), ("n_blocks", C.c_uint32), ("n_blocks_alloc", C.c_uint32), ("q", C.c_int32),
+        ("pop_in", C.c_void_p), ("pop_out", C.c_void_p), ("flags", C.c_void_p), ("info", C.c_void_p),
+        ("n_blocks", C.c_uint32), ("n_blocks_alloc", C.c_uint32), ("n_down", C.c_uint32), ("n_up", C.c_uint32),
+        ("gnx", C.c_int32), ("gny", C.c_int32), ("gnz", C.c_int32),
     ]
+
+    def clone(self) -> "BlockDesc":
+        d = BlockDesc()
+        C.memmove(C.byref(d), C.byref(self), C.sizeof(BlockDesc))
+        return d
 
 
 _P = C.c_void_p
@@ -95,6 +100,15 @@ _SIGNATURES = {
     "nlbm_dense_halo_push": (C.c_int, [_D, _P, _D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "nlbm_dense_halo_pack": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_size_t), _P]),
     "nlbm_dense_halo_unpack": (C.c_int, [_D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "nlbm_block_classify": (C.c_int, [_B, C.c_int, C.POINTER(C.c_double), _P, _P]),
+    "nlbm_block_wall_mask": (C.c_int, [_B, C.c_int, _P, _P]),
+    "nlbm_block_init_pop_f32": (C.c_int, [_B, C.c_int, C.c_double, _P]),
+    "nlbm_block_init_pop_f64": (C.c_int, [_B, C.c_int, C.c_double, _P]),
+    "nlbm_d3q19_f32_block_step": (C.c_int, [_B, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_d3q19_f64_block_step": (C.c_int, [_B, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_d3q27_f32_block_step": (C.c_int, [_B, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_d3q27_f64_block_step": (C.c_int, [_B, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_block_halo_push": (C.c_int, [_B, _P, _B, _P, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "nlbm_ipc_export": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_uint64)]),
     "nlbm_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "nlbm_ipc_close": (C.c_int, [_P]),

@@ -28,7 +28,8 @@ UNITS = {
     "lbm_step_ref.cu": ["-fmad=false"],
     "lbm_setup.cu": ["-fmad=false"],
     "lbm_halo.cu": [],
-    "lbm_block.cu": [],
+    "lbm_block_fast.cu": [],
+    "lbm_block_ref.cu": ["-fmad=false"],
 }
 
 

@@ -7,6 +7,7 @@
 
 #include <cuda.h>
 
+#include "lbm_block.cuh"
 #include "lbm_common.cuh"
 #include "lbm_host.h"
 
@@ -435,6 +436,149 @@ int nlbm_dense_halo_unpack(const nlbm_dense_desc* d, void* field, int elem_bytes
     }
     cudaError_t e = nlbm::launchPlaneCopy(buffer, field, pl, planeBytes, (cudaStream_t)stream);
     return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo unpack launch");
+}
+
+// ------------------------------------------------------------------------------------------------ block-sparse path
+static int checkBlockDesc(const nlbm_block_desc* d, bool needIn, bool needOut, bool needFlags)
+{
+    if (!d)
+        return fail(NLBM_ERR_INVALID, "null descriptor");
+    if (d->n_blocks > d->n_blocks_alloc || d->n_blocks_alloc == 0xFFFFFFFFu)
+        return fail(NLBM_ERR_INVALID, "bad block counts %u local of %u allocated", d->n_blocks, d->n_blocks_alloc);
+    if ((uint64_t)d->n_down + d->n_up > d->n_blocks)
+        return fail(NLBM_ERR_INVALID, "boundary layers (%u + %u blocks) exceed the %u local blocks", d->n_down, d->n_up, d->n_blocks);
+    if (!d->info || ((uintptr_t)d->info & 127))
+        return fail(NLBM_ERR_INVALID, "info null or not 128-byte aligned");
+    if (needIn && (!d->pop_in || ((uintptr_t)d->pop_in & 127)))
+        return fail(NLBM_ERR_INVALID, "pop_in null or not 128-byte aligned");
+    if (needOut && (!d->pop_out || ((uintptr_t)d->pop_out & 127)))
+        return fail(NLBM_ERR_INVALID, "pop_out null or not 128-byte aligned");
+    if (needFlags && (!d->flags || ((uintptr_t)d->flags & 127)))
+        return fail(NLBM_ERR_INVALID, "flags null or not 128-byte aligned");
+    if (needIn && needOut && d->pop_in == d->pop_out)
+        return fail(NLBM_ERR_INVALID, "pop_in and pop_out alias (the pull scheme needs two fields, LbmIteration.h:38-39)");
+    return NLBM_OK;
+}
+
+static int blockStepImpl(nlbm::StepKind kind, const nlbm_block_desc* d, double omega, int view, int opts, void* stream)
+{
+    if (int rc = checkBlockDesc(d, true, true, true))
+        return rc;
+    if (view < NLBM_VIEW_STANDARD || view > NLBM_VIEW_BOUNDARY)
+        return fail(NLBM_ERR_INVALID, "bad data view %d", view);
+    const int arith = opts & 0xF;
+    if (arith != NLBM_ARITH_REFERENCE && arith != NLBM_ARITH_FAST)
+        return fail(NLBM_ERR_INVALID, "bad arithmetic mode %d", arith);
+    nlbm::BlockArgs a;
+    a.in = d->pop_in;
+    a.out = d->pop_out;
+    a.flags = d->flags;
+    a.info = d->info;
+    a.popPitch = (int64_t)d->n_blocks_alloc * nlbm::kBlockCells;
+    a.omega = omega;
+    cudaStream_t st = (cudaStream_t)stream;
+    // block ranges of the view: [0, n_down) lowest layer, [n_blocks - n_up, n_blocks) highest layer
+    uint32_t ranges[2][2] = {{0, d->n_blocks}, {0, 0}};
+    if (view == NLBM_VIEW_INTERNAL) {
+        ranges[0][0] = d->n_down;
+        ranges[0][1] = d->n_blocks - d->n_down - d->n_up;
+    } else if (view == NLBM_VIEW_BOUNDARY) {
+        ranges[0][1] = d->n_down;
+        ranges[1][0] = d->n_blocks - d->n_up;
+        ranges[1][1] = d->n_up;
+    }
+    for (auto& r : ranges) {
+        if (r[1] == 0)
+            continue;
+        a.firstBlock = r[0];
+        cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchBlockStepRef(kind, a, r[1], st) : nlbm::launchBlockStepFast(kind, a, r[1], st);
+        if (e != cudaSuccess)
+            return cudaFail(e, "block step launch");
+    }
+    return NLBM_OK;
+}
+
+int nlbm_d3q19_f32_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return blockStepImpl(nlbm::kD3Q19_F32, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q19_f64_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return blockStepImpl(nlbm::kD3Q19_F64, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q27_f32_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return blockStepImpl(nlbm::kD3Q27_F32, d, omega, data_view, opts, stream);
+}
+int nlbm_d3q27_f64_block_step(const nlbm_block_desc* d, double omega, int data_view, int opts, void* stream)
+{
+    return blockStepImpl(nlbm::kD3Q27_F64, d, omega, data_view, opts, stream);
+}
+
+int nlbm_block_classify(const nlbm_block_desc* d, int geom, const double* sphere, const uint32_t* active_mask, void* stream)
+{
+    if (int rc = checkBlockDesc(d, false, false, true))
+        return rc;
+    if (geom < 0 || geom > 2)
+        return fail(NLBM_ERR_INVALID, "bad geometry %d", geom);
+    cudaError_t e = nlbm::launchBlockClassify(*d, geom, sphere, active_mask, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "block classify launch");
+}
+
+int nlbm_block_wall_mask(const nlbm_block_desc* d, int q, int32_t* d_bad, void* stream)
+{
+    if (int rc = checkBlockDesc(d, false, false, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchBlockWallMask(*d, q, d_bad, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "block wall mask launch");
+}
+
+int nlbm_block_init_pop_f32(const nlbm_block_desc* d, int q, double ulb, void* stream)
+{
+    if (int rc = checkBlockDesc(d, false, true, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchBlockInitPop<float>(*d, q, ulb, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "block init launch");
+}
+int nlbm_block_init_pop_f64(const nlbm_block_desc* d, int q, double ulb, void* stream)
+{
+    if (int rc = checkBlockDesc(d, false, true, true))
+        return rc;
+    if (q != 19 && q != 27)
+        return fail(NLBM_ERR_INVALID, "lattice must be 19 or 27");
+    cudaError_t e = nlbm::launchBlockInitPop<double>(*d, q, ulb, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "block init launch");
+}
+
+int nlbm_block_halo_push(const nlbm_block_desc* s, const void* src_field, const nlbm_block_desc* t, void* dst_field,
+                         uint32_t dst_first_ghost, int elem_bytes, int ncomp, int lattice_q, int dir, void* stream)
+{
+    if (int rc = checkBlockDesc(s, false, false, false))
+        return rc;
+    if (int rc = checkBlockDesc(t, false, false, false))
+        return rc;
+    if (!src_field || !dst_field)
+        return fail(NLBM_ERR_INVALID, "null field");
+    if (elem_bytes != 4 && elem_bytes != 8)
+        return fail(NLBM_ERR_INVALID, "elem_bytes must be 4 or 8");
+    if (dir != 1 && dir != -1)
+        return fail(NLBM_ERR_INVALID, "dir must be +1 or -1");
+    if (!(lattice_q == 0 || lattice_q == 19 || lattice_q == 27) || ncomp < 1 || ncomp > 27 || (lattice_q && ncomp != lattice_q))
+        return fail(NLBM_ERR_INVALID, "bad component count %d / lattice %d", ncomp, lattice_q);
+    const uint32_t n = dir > 0 ? s->n_up : s->n_down;
+    if ((uint64_t)dst_first_ghost + n > t->n_blocks_alloc || dst_first_ghost < t->n_blocks)
+        return fail(NLBM_ERR_INVALID, "ghost range [%u, %u) outside the destination's ghost blocks", dst_first_ghost, dst_first_ghost + n);
+    int       list[27];
+    const int nc = crossing(lattice_q, ncomp, dir, list);
+    const uint32_t first = dir > 0 ? s->n_blocks - s->n_up : 0;
+    cudaError_t    e = nlbm::launchBlockSliceCopy(src_field, dst_field, elem_bytes, list, nc, (int64_t)s->n_blocks_alloc * 512,
+                                                  (int64_t)t->n_blocks_alloc * 512, first, dst_first_ghost, n, dir > 0 ? 7 : 0,
+                                                  (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "block halo push launch");
 }
 
 int nlbm_ipc_export(const void* ptr, unsigned char* handle64, uint64_t* offset)

@@ -37,6 +37,56 @@ cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, siz
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- block-sparse faces
+// One z-slice (64 cells = 256 / 512 contiguous bytes) of every boundary block and crossing population.
+struct SliceArgs
+{
+    int      comps[27];
+    int      ncomps;
+    int64_t  srcPopPitch, dstPopPitch;  // bytes
+    uint32_t srcFirst, dstFirst, nBlocks;
+    int      sliceOff, vecPerSlice;     // byte offset of the slice inside a block tile, 16-byte vectors per slice
+    int      blockBytes;
+};
+__global__ void __launch_bounds__(256) k_block_slice_copy(const char* __restrict__ src, char* __restrict__ dst, const SliceArgs s)
+{
+    const int64_t total = (int64_t)s.nBlocks * s.vecPerSlice;
+    const int     c = blockIdx.y;
+    const char*   sp = src + s.comps[c] * s.srcPopPitch + (int64_t)s.srcFirst * s.blockBytes + s.sliceOff;
+    char*         dp = dst + s.comps[c] * s.dstPopPitch + (int64_t)s.dstFirst * s.blockBytes + s.sliceOff;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / s.vecPerSlice, v = i - b * s.vecPerSlice;
+        const int64_t o = b * s.blockBytes + v * 16;
+        *reinterpret_cast<uint4*>(dp + o) = __ldcs(reinterpret_cast<const uint4*>(sp + o));
+    }
+}
+
+cudaError_t launchBlockSliceCopy(const void* src, void* dst, int elemBytes, const int* comps, int ncomps, int64_t srcPopPitch,
+                                 int64_t dstPopPitch, uint32_t srcFirst, uint32_t dstFirst, uint32_t nBlocks, int zSlice, cudaStream_t st)
+{
+    if (nBlocks == 0 || ncomps == 0)
+        return cudaSuccess;
+    SliceArgs s;
+    for (int i = 0; i < ncomps; ++i)
+        s.comps[i] = comps[i];
+    s.ncomps = ncomps;
+    s.srcPopPitch = srcPopPitch * elemBytes;
+    s.dstPopPitch = dstPopPitch * elemBytes;
+    s.srcFirst = srcFirst;
+    s.dstFirst = dstFirst;
+    s.nBlocks = nBlocks;
+    s.blockBytes = 512 * elemBytes;
+    s.sliceOff = zSlice * 64 * elemBytes;
+    s.vecPerSlice = 64 * elemBytes / 16;
+    const int64_t total = (int64_t)nBlocks * s.vecPerSlice;
+    int64_t       bx = (total + 255) / 256;
+    if (bx > 148 * 4)
+        bx = 148 * 4;
+    dim3 grid((unsigned)bx, ncomps);
+    k_block_slice_copy<<<grid, 256, 0, st>>>((const char*)src, (char*)dst, s);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- device-side ordering between GPUs
 // One process per GPU cannot order a neighbour's stream with CUDA events without a host hand-shake per iteration.  The
 // peer-store halo transport therefore orders with flag words: after its face copy (stream order) the sender publishes a

@@ -36,7 +36,18 @@ cudaError_t launchInitPop(const nlbm_dense_desc& d, int q, double ulb, cudaStrea
 template <typename S, typename C>
 cudaError_t launchRhoU(const nlbm_dense_desc& d, void* rho, void* u, cudaStream_t st);
 
+// lbm_block_ref.cu / lbm_block_fast.cu
+struct BlockArgs;
+cudaError_t launchBlockStepRef(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st);
+cudaError_t launchBlockStepFast(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st);
+cudaError_t launchBlockClassify(const nlbm_block_desc& d, int geom, const double* sphere, const uint32_t* activeMask, cudaStream_t st);
+cudaError_t launchBlockWallMask(const nlbm_block_desc& d, int q, int32_t* bad, cudaStream_t st);
+template <typename S>
+cudaError_t launchBlockInitPop(const nlbm_block_desc& d, int q, double ulb, cudaStream_t st);
+
 // lbm_halo.cu
+cudaError_t launchBlockSliceCopy(const void* src, void* dst, int elemBytes, const int* comps, int ncomps, int64_t srcPopPitch,
+                                 int64_t dstPopPitch, uint32_t srcFirst, uint32_t dstFirst, uint32_t nBlocks, int zSlice, cudaStream_t st);
 struct PlaneList
 {
     int     n;

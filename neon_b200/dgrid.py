@@ -69,6 +69,8 @@ def _aligned_zeros(n: int, dtype: torch.dtype, device: torch.device, align: int 
 
 
 class dGrid:
+    kind = "dense"
+
     def __init__(self, backend: Backend, dim: Sequence[int], stencil_radius: int = 1,
                  partition: Optional[Tuple[int, int]] = None):
         """``partition=(index, count)`` places an arbitrary slab of a ``count``-way split on THIS process's device —

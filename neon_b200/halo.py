@@ -42,6 +42,8 @@ class HaloUpdateContainer(Container):
             transport = os.environ.get("NEON_B200_HALO", "ipc") if bk.runtime == Runtime.stream else "views"
         if transport not in ("packed", "views", "ipc"):
             raise ValueError(transport)
+        if getattr(field.grid, "kind", "dense") == "block" and transport != "ipc":
+            raise ValueError("block-sparse fields exchange their faces through the peer-store transport (\"ipc\") only")
         if transport != "views" and bk.runtime != Runtime.stream:
             raise ValueError(f"transport {transport!r} needs CUDA")
         self.transport = transport
@@ -56,6 +58,9 @@ class HaloUpdateContainer(Container):
         return list(range(self.field.cardinality))
 
     def bytesPerDirection(self, direction: int) -> int:
+        g = self.field.grid
+        if getattr(g, "kind", "dense") == "block":  # one z-slice of 64 cells per boundary block
+            return len(self.components(direction)) * (g.n_up if direction > 0 else g.n_down) * 64 * self.field.elem_bytes
         return len(self.components(direction)) * self.field.pitch_z * self.field.elem_bytes
 
     # ------------------------------------------------------------------------------------------------------------

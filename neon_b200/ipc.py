@@ -59,7 +59,9 @@ class IpcHalo:
         self.err = torch.zeros(1, dtype=torch.int32, device=bk.device)
         torch.cuda.synchronize(bk.device)
         # every rank publishes (field, flags) handles; each maps only its neighbours' allocations
-        mine = (export_ptr(f.data.data_ptr()), export_ptr(self.flags.data_ptr()))
+        self.block = getattr(g, "kind", "dense") == "block"
+        shape = (g.n_blocks, g.n_blocks_alloc, g.n_ghost_down, g.n_down, g.n_up) if self.block else None
+        mine = (export_ptr(f.data.data_ptr()), export_ptr(self.flags.data_ptr()), shape)
         handles = [None] * bk.world
         dist.all_gather_object(handles, mine, group=bk.group)
         dn, up = g.neighbours()
@@ -67,9 +69,9 @@ class IpcHalo:
         for nbr in (dn, up):
             if nbr is None:
                 continue
-            hf, hg = handles[nbr]
+            hf, hg, _ = handles[nbr]
             self.peer[nbr] = (import_ptr(*hf), import_ptr(*hg))  # addresses aliasing the neighbour's memory
-        self._descs = self._neighbour_descs()
+        self._descs = self._neighbour_block_descs(handles) if self.block else self._neighbour_descs()
         bk.barrier()
 
     def _neighbour_descs(self):
@@ -84,6 +86,20 @@ class IpcHalo:
             d.pitch_q = d.pitch_z * (d.nz_local + 2 * d.z_halo)
             d.pop_in = None
             out[nbr] = d
+        return out
+
+    def _neighbour_block_descs(self, handles):
+        """Block counts of each neighbour and where my faces land among its ghost blocks."""
+        g = self.halo.field.grid
+        out = {}
+        for nbr in self.peer:
+            n_blocks, n_alloc, n_ghost_down, n_down, n_up = handles[nbr][2]
+            d = g.desc(None, None, None).clone()
+            d.n_blocks, d.n_blocks_alloc, d.n_down, d.n_up = n_blocks, n_alloc, n_down, n_up
+            # pushing up lands in the upper neighbour's ghost-DOWN blocks (they come first), pushing down in the lower
+            # neighbour's ghost-UP blocks (after its ghost-down ones)
+            first_ghost = n_blocks if nbr > g.part else n_blocks + n_ghost_down
+            out[nbr] = (d, first_ghost)
         return out
 
     def run(self, streamIdx: int) -> None:
@@ -102,7 +118,11 @@ class IpcHalo:
             if nbr is None:
                 continue
             pf, pg = self.peer[nbr]
-            capi.call("nlbm_dense_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(self._descs[nbr]), pf, *args, direction, st)
+            if self.block:
+                dd, first_ghost = self._descs[nbr]
+                capi.call("nlbm_block_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(dd), pf, first_ghost, *args, direction, st)
+            else:
+                capi.call("nlbm_dense_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(self._descs[nbr]), pf, *args, direction, st)
             capi.call("nlbm_flag_signal", pg + 4 * slot, k, st)
         # wait for what the neighbours pushed into my ghost planes
         for nbr, slot in ((dn, FROM_BELOW), (up, FROM_ABOVE)):

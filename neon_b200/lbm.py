@@ -28,9 +28,13 @@ def omega_from_re(n: int, re: float = 100.0, ulb: float = 0.04) -> float:
     return 1.0 / (3.0 * nu + 0.5)
 
 
-def _step_symbol(q: int, store: np.dtype, compute: Optional[np.dtype]) -> str:
+def _step_symbol(q: int, store: np.dtype, compute: Optional[np.dtype], kind: str = "dense") -> str:
     store = np.dtype(store)
     compute = store if compute is None else np.dtype(compute)
+    if kind == "block":
+        if store == compute and store in (np.float32, np.float64):
+            return f"nlbm_d3q{q}_{'f32' if store == np.float32 else 'f64'}_block_step"
+        raise ValueError(f"unsupported bGrid D3Q{q} store/compute pair {store}/{compute}")
     if store == np.float32 and compute == np.float32:
         return f"nlbm_d3q{q}_f32_dense_step"
     if store == np.float64 and compute == np.float64:
@@ -50,7 +54,7 @@ class LbmContainers:
         if fIn is fOut:
             raise capi.NeonException("LbmContainers.iteration", capi.ERR_INVALID, "fIn and fOut must be two fields")
         grid = fIn.grid
-        sym = _step_symbol(lattice_q, fIn.dtype, compute)
+        sym = _step_symbol(lattice_q, fIn.dtype, compute, getattr(grid, "kind", "dense"))
         if fIn.cardinality != lattice_q or fOut.cardinality != lattice_q or fOut.dtype != fIn.dtype:
             raise capi.NeonException("LbmContainers.iteration", capi.ERR_INVALID, "population fields do not match the lattice")
         desc = grid.desc(fIn, fOut, cellTypeField)

@@ -71,11 +71,11 @@ def init_populations(field: dField, flag: FlagField, q: int, ulb: float = 0.04, 
     """Device-side initial populations of ``field`` (all planes, ghosts included) from the classes in ``flag``."""
     g = field.grid
     d = g.desc(None, field, flag)
-    sym = "nlbm_dense_init_pop_f32" if field.dtype == np.float32 else "nlbm_dense_init_pop_f64"
+    sym = f"nlbm_{g.kind}_init_pop_f32" if field.dtype == np.float32 else f"nlbm_{g.kind}_init_pop_f64"
     capi.call(sym, C.byref(d), q, ulb, g.backend.streamHandle(stream_idx))
 
 
-def setup_device(grid: dGrid, q: int, dtype, geom: int = CAVITY, sphere=None, ulb: float = 0.04):
+def setup_device(grid, q: int, dtype, geom: int = CAVITY, sphere=None, ulb: float = 0.04):
     """Everything on the device: (pop0, pop1, flag) ready to iterate."""
     pop0 = grid.newField("pop0", q, dtype)
     pop1 = grid.newField("pop1", q, dtype)
@@ -87,7 +87,7 @@ def setup_device(grid: dGrid, q: int, dtype, geom: int = CAVITY, sphere=None, ul
     return pop0, pop1, flag
 
 
-def setup_host(grid: dGrid, q: int, dtype, cls: np.ndarray, pop: np.ndarray):
+def setup_host(grid, q: int, dtype, cls: np.ndarray, pop: np.ndarray):
     """The reference's flow: host arrays -> updateDeviceData -> wall mask on the device (RunCavityTwoPop.cu:226-241)."""
     pop0 = grid.newField("pop0", q, dtype)
     pop1 = grid.newField("pop1", q, dtype)

@@ -1,6 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multiproc.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/pytest.log
-CUDA_LAUNCH_BLOCKING=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_debug.py ipc > gpurun_out/dbg_ipc.log 2>&1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 tests/mgpu_check.py > gpurun_out/mgpu2.log 2>&1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 50 --warmup 5 --transport ipc > gpurun_out/bench2_ipc.json 2> gpurun_out/bench2_ipc.err
+timeout 900 python -m pytest tests/test_gpu_block.py -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_block.log
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > gpurun_out/pytest.log
+: > gpurun_out/bench_var.log
+for v in "--workload bcavity256" "--workload bcavity512" "--workload sphere" "--workload bcavity512 --arith reference"; do
+  echo "== $v" >> gpurun_out/bench_var.log
+  timeout 300 python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu $v 2>&1 | tail -3 >> gpurun_out/bench_var.log
+done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_block_step -s 2 -c 1 -o gpurun_out/prof_block_r1a -f \
+  python bench.py --steps 3 --warmup 1 --no-e2e --no-cpu --workload bcavity512 > gpurun_out/ncu_full.log 2>&1

@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, results):
+def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, results):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -35,7 +35,7 @@ def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, results):
         from neon_b200 import problems as P
         dtype = np.dtype(dtype_name)
         bk = nb.Backend(devices=[0] * world)
-        grid = nb.dGrid(bk, dim)
+        grid = nb.dGrid(bk, dim) if kind == "dGrid" else nb.bGrid(bk, dim)
         pop0, pop1, flag = P.setup_device(grid, q, dtype, P.CAVITY_SPHERE)
         it = nb.LbmIteration(nb.StencilSemantic.streaming, getattr(nb.Occ, occ_name), nb.TransferMode.get, pop0, pop1, flag, 1.25,
                              lattice_q=q, arith=nb.ARITH_REFERENCE, halo_transport="ipc")
@@ -52,14 +52,16 @@ def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("q,dtype,world,occ", [(19, "float32", 2, "standard"), (19, "float32", 3, "none"), (27, "float64", 2, "standard")])
-def test_ipc_halo_across_processes(oracle, q, dtype, world, occ):
+@pytest.mark.parametrize("q,dtype,world,occ,kind", [(19, "float32", 2, "standard", "dGrid"), (19, "float32", 3, "none", "dGrid"),
+                                                     (27, "float64", 2, "standard", "dGrid"), (19, "float32", 2, "standard", "bGrid"),
+                                                     (27, "float64", 2, "none", "bGrid")])
+def test_ipc_halo_across_processes(oracle, q, dtype, world, occ, kind):
     if not torch.cuda.is_available():
         pytest.fail("gpu tests need a CUDA device")
-    dim, iters = (36, 20, 23), 8
+    dim, iters = ((36, 20, 23) if kind == "dGrid" else (36, 20, 37)), 8
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), q, dtype, dim, iters, occ, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), q, dtype, dim, iters, occ, kind, results), nprocs=world, join=True)
     nx, ny, nz = dim
     cls = oracle.classify(1, nx, ny, nz)
     mask = oracle.wall_mask(q, cls)

@@ -491,6 +491,7 @@ static int blockStepImpl(nlbm::StepKind kind, const nlbm_block_desc* d, double o
         if (r[1] == 0)
             continue;
         a.firstBlock = r[0];
+        a.nBlocks = r[1];
         cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchBlockStepRef(kind, a, r[1], st) : nlbm::launchBlockStepFast(kind, a, r[1], st);
         if (e != cudaSuccess)
             return cudaFail(e, "block step launch");

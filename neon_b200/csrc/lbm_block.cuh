@@ -13,11 +13,12 @@
 // (reference: [blk][q][z][y][x] with 32-bit offsets, connectivity / origin / active-mask in three separate arrays.)
 //
 // Kernel: one CTA per block, one thread per VEC consecutive cells of a row (fp32: VEC = 4, 128 threads).  As in the
-// dense kernel every load is a predicated volatile PTX load issued before anything is consumed, in two waves: wave 1 — the
-// block's info line, its flag words and every population row that lies inside the block itself (about 85 % of the bytes,
-// addresses need no table); wave 2, once the info line is there — the rows and the x-face scalars that live in
-// neighbouring blocks.  The x shift inside a row is a warp shuffle.  Fix-ups, collision and the single store per
-// population are the dense kernel's (finishCells semantics) with block-aware addressing.
+// dense kernel every load is a predicated volatile PTX load issued before anything is consumed.  The block's info line
+// gates the neighbour addresses; it is prefetched into L2 by the CTA that ran ~one chip-load of blocks earlier, so that it
+// costs an L2 hit, not a DRAM round trip, in front of the population loads.  (A first version issued the rows inside the
+// block before the info line arrived and the others after: ptxas serialises the two predicated loads of a row on their
+// shared destination registers, ncu r01i.)  The x shift inside a row is a warp shuffle.  Fix-ups, collision and the
+// single store per population are the dense kernel's (finishCells semantics) with block-aware addressing.
 #pragma once
 #include "lbm_step.cuh"
 
@@ -26,6 +27,7 @@ namespace nlbm {
 constexpr int      kB = 8;                  // block edge (Neon::bGrid = StaticBlock<8,8,8>, domain/bGrid.h:5)
 constexpr int      kBlockCells = kB * kB * kB;
 constexpr uint32_t kNoBlock = NLBM_NO_BLOCK;
+constexpr uint32_t kPrefetchAhead = 148 * 6;  // ~ the CTAs resident on the chip: whose info line to pull into L2
 
 struct BlockArgs
 {
@@ -34,37 +36,10 @@ struct BlockArgs
     const uint32_t* flags;
     const uint32_t* info;
     uint32_t        firstBlock;  // the view's first block
+    uint32_t        nBlocks;     // blocks of this launch
     int64_t         popPitch;    // elements between populations = n_blocks_alloc * 512
     double          omega;
 };
-
-// keep-variants of the predicated loads (wave 2 must not clear what wave 1 fetched)
-__device__ __forceinline__ void ldPredKeep(const float* p, bool pred, float (&v)[4])
-{
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\n@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n}\n"
-                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])
-                 : "l"(p), "r"((uint32_t)pred));
-}
-__device__ __forceinline__ void ldPredKeep(const float* p, bool pred, float (&v)[2])
-{
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q ld.global.nc.v2.f32 {%0, %1}, [%2];\n}\n"
-                 : "+f"(v[0]), "+f"(v[1])
-                 : "l"(p), "r"((uint32_t)pred));
-}
-__device__ __forceinline__ void ldPredKeep(const float* p, bool pred, float (&v)[1])
-{
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f32 %0, [%1];\n}\n" : "+f"(v[0]) : "l"(p), "r"((uint32_t)pred));
-}
-__device__ __forceinline__ void ldPredKeep(const double* p, bool pred, double (&v)[2])
-{
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q ld.global.nc.v2.f64 {%0, %1}, [%2];\n}\n"
-                 : "+d"(v[0]), "+d"(v[1])
-                 : "l"(p), "r"((uint32_t)pred));
-}
-__device__ __forceinline__ void ldPredKeep(const double* p, bool pred, double (&v)[1])
-{
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(v[0]) : "l"(p), "r"((uint32_t)pred));
-}
 
 // Address of cell (x, y, z) — each coordinate in [-1, 8] — of population plane `base` (already offset to population q and
 // block 0), seen from block `blk` whose info line is spread over the warp (lane i holds word i).
@@ -90,42 +65,28 @@ struct BlockCfg
     static constexpr int MIN_BLOCKS = MIN_BLOCKS_ < 1 ? 1 : MIN_BLOCKS_;
 };
 
-// ---- wave 1 / wave 2 loads of population q
+// ---- loads of population q: the row (y - c_y, z - c_z) of this block or of the neighbour that holds it, plus, on the
+// first / last lane of a row, the one cell of the x-neighbour block a shuffle cannot supply
 template <class L, int q, typename T, int VEC>
-__device__ __forceinline__ void blockLoadInside(const T* __restrict__ popIn, const BlockArgs& a, const uint32_t blk, const int x0,
-                                                const int y, const int z, T (&v)[VEC])
-{
-    constexpr int cy = L::c(q, 1), cz = L::c(q, 2);
-    const int     ys = y - cy, zs = z - cz;
-    const bool    inside = (cy == 0 || (unsigned)ys < (unsigned)kB) && (cz == 0 || (unsigned)zs < (unsigned)kB);
-    const T*      p = popIn + q * a.popPitch + (int64_t)blk * kBlockCells + (zs * (kB * kB) + ys * kB + x0);
-    ldPred(p, inside, v);
-}
-
-template <class L, int q, typename T, int VEC>
-__device__ __forceinline__ void blockLoadOutside(const T* __restrict__ popIn, const BlockArgs& a, const uint32_t blk,
-                                                 const uint32_t infoWord, const int tx, const int x0, const int y, const int z,
-                                                 T (&v)[VEC], T& edge)
+__device__ __forceinline__ void blockLoad(const T* __restrict__ popIn, const BlockArgs& a, const uint32_t blk, const uint32_t infoWord,
+                                          const int tx, const int x0, const int y, const int z, T (&v)[VEC], T& edge)
 {
     constexpr int cx = L::c(q, 0), cy = L::c(q, 1), cz = L::c(q, 2);
     constexpr int LPR = kB / VEC;
     const int     ys = y - cy, zs = z - cz;
     const T*      base = popIn + q * a.popPitch;
-    if constexpr (cy != 0 || cz != 0) {
-        const bool inside = (cy == 0 || (unsigned)ys < (unsigned)kB) && (cz == 0 || (unsigned)zs < (unsigned)kB);
-        bool       ex;
-        const T*   p = cellOf<T>(base, blk, infoWord, x0, ys, zs, ex);
-        ldPredKeep(p, !inside && ex, v);
-    }
+    bool          ex;
+    const T*      p = cellOf<T>(base, blk, infoWord, x0, ys, zs, ex);
+    ldPred(p, ex, v);
     edge = T(0);
     if constexpr (cx == 1) {  // cell x0 pulls from x0 - 1: the first lane of a row needs x = -1 of the row (ys, zs)
-        bool     ex;
-        const T* p = cellOf<T>(base, blk, infoWord, -1, ys, zs, ex);
-        edge = ldPred1(p, tx == 0 && ex);
+        bool     exe;
+        const T* pe = cellOf<T>(base, blk, infoWord, -1, ys, zs, exe);
+        edge = ldPred1(pe, tx == 0 && exe);
     } else if constexpr (cx == -1) {
-        bool     ex;
-        const T* p = cellOf<T>(base, blk, infoWord, kB, ys, zs, ex);
-        edge = ldPred1(p, tx == LPR - 1 && ex);
+        bool     exe;
+        const T* pe = cellOf<T>(base, blk, infoWord, kB, ys, zs, exe);
+        edge = ldPred1(pe, tx == LPR - 1 && exe);
     }
 }
 
@@ -154,17 +115,11 @@ __device__ __forceinline__ void blockShift(const int tx, T (&v)[VEC], const T ed
 }
 
 template <class L, typename T, int VEC, int... Qs>
-__device__ __forceinline__ void blockLoadInsideAll(std::integer_sequence<int, Qs...>, const T* __restrict__ popIn, const BlockArgs& a,
-                                                   const uint32_t blk, const int x0, const int y, const int z, T (&f)[L::Q][VEC])
+__device__ __forceinline__ void blockLoadAll(std::integer_sequence<int, Qs...>, const T* __restrict__ popIn, const BlockArgs& a,
+                                             const uint32_t blk, const uint32_t infoWord, const int tx, const int x0, const int y,
+                                             const int z, T (&f)[L::Q][VEC], T (&edge)[L::Q])
 {
-    (blockLoadInside<L, Qs, T, VEC>(popIn, a, blk, x0, y, z, f[Qs]), ...);
-}
-template <class L, typename T, int VEC, int... Qs>
-__device__ __forceinline__ void blockLoadOutsideAll(std::integer_sequence<int, Qs...>, const T* __restrict__ popIn, const BlockArgs& a,
-                                                    const uint32_t blk, const uint32_t infoWord, const int tx, const int x0, const int y,
-                                                    const int z, T (&f)[L::Q][VEC], T (&edge)[L::Q])
-{
-    (blockLoadOutside<L, Qs, T, VEC>(popIn, a, blk, infoWord, tx, x0, y, z, f[Qs], edge[Qs]), ...);
+    (blockLoad<L, Qs, T, VEC>(popIn, a, blk, infoWord, tx, x0, y, z, f[Qs], edge[Qs]), ...);
 }
 template <class L, typename T, int VEC, int... Qs>
 __device__ __forceinline__ void blockShiftAll(std::integer_sequence<int, Qs...>, const int tx, T (&f)[L::Q][VEC], const T (&edge)[L::Q])
@@ -257,15 +212,17 @@ __global__ void __launch_bounds__(BlockCfg<COL, T, VEC>::THREADS, BlockCfg<COL, 
     const int64_t  cellOff = (int64_t)blk * kBlockCells + (z * (kB * kB) + y * kB + x0);
     const T*       popIn = reinterpret_cast<const T*>(a.in);
 
-    // ---- wave 1: info line, flag words, every row that lives in this block
+    // the block's info line (one 128-byte line: lane i holds word i) gates every neighbour address; the CTA that ran
+    // kPrefetchAhead blocks earlier pulled it into L2, and this one does the same for a later block
     uint32_t infoWord;
     asm volatile("ld.global.nc.u32 %0, [%1];\n" : "=r"(infoWord) : "l"(a.info + (int64_t)blk * 32 + lane));
+    if (t == 0 && blockIdx.x + kPrefetchAhead < a.nBlocks)
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.info + ((int64_t)blk + kPrefetchAhead) * 32));
     uint32_t fl[VEC];
     ldFlags<VEC>(a.flags + cellOff, fl);
+    // every population load of the thread goes out before anything is consumed
     T f[Q][VEC], edge[Q];
-    blockLoadInsideAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, popIn, a, blk, x0, y, z, f);
-    // ---- wave 2: rows and x-face scalars held by neighbouring blocks
-    blockLoadOutsideAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, popIn, a, blk, infoWord, tx, x0, y, z, f, edge);
+    blockLoadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, popIn, a, blk, infoWord, tx, x0, y, z, f, edge);
 
     bool plain = true, anyBulk = false, allBulk = true;
 #pragma unroll

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--tma-groups", type=int, default=0)
     ap.add_argument("--rows-log2", type=int, default=0)
     ap.add_argument("--flags-summary-first", action="store_true")
+    ap.add_argument("--rpw", type=int, default=0, help="rows per warp selector: 0 default, else log2(rows)+1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")
@@ -229,7 +230,7 @@ def main():
     omega = wl.get("omega", nb.omega_from_re(dim[0]))
     arith = nb.ARITH_FAST if args.arith == "fast" else nb.ARITH_REFERENCE
     opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[args.kernel]) \
-        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0)
+        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0) | ((args.rpw & 7) << 21)
     occ = nb.Occ.standard if args.occ == "standard" else nb.Occ.none
 
     bk = nb.Backend()

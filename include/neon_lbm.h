@@ -85,6 +85,9 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * cell (saves up to 4 B/cell of traffic).  Default (bit clear): the flag words travel with the populations — one dependent
  * memory round trip less for warps that touch walls, measured faster on B200.                                          */
 #define NLBM_OPT_FLAGS_SUMMARY_FIRST (1 << 20)
+/* bits 21..23 (direct kernel): rows a warp covers, 0 = library default, else log2(rows) + 1 (1: whole-row warps of 32 lanes,
+ * 3: 4 rows x 8 lanes ...).  Narrow warp tiles keep the wall round trip away from most warps.  Never changes results.      */
+#define NLBM_OPT_ROWS_PER_WARP_LOG2P1(r) (((r)&0x7) << 21)
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2

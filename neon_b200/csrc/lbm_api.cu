@@ -152,6 +152,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
     a.omega = omega;
     a.flagsAlways = ((opts >> 20) & 1) ? 0 : 1;
+    a.lprLog2 = 5;
     // Views split at stencil radius 1 (both lattices): INTERNAL = local z in [1, nz-1), BOUNDARY = {0, nz-1}
     // (the reference's BOUNDARY span folds wrongly; this is the intended cover).
     const int r = 1, nz = d->nz_local;
@@ -175,6 +176,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     l.nzView = nzView;
     l.vec = (opts >> 4) & 0xF;
     l.rowsLog2 = (opts >> 8) & 0xF;
+    l.rpwSel = (opts >> 21) & 0x7;
     l.tmapA = nullptr;
     l.tmapB = nullptr;
     l.tmapF = nullptr;

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(BlockCfg<COL, T, VEC>::THREADS, BlockCfg<COL, 
     if (t == 0 && blockIdx.x + kPrefetchAhead < a.nBlocks)
         asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.info + ((int64_t)blk + kPrefetchAhead) * 32));
     uint32_t fl[VEC];
-    ldFlags<VEC>(a.flags + cellOff, fl);
+    ldFlags<VEC>(a.flags + cellOff, true, fl);
     // every population load of the thread goes out before anything is consumed
     T f[Q][VEC], edge[Q];
     blockLoadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, popIn, a, blk, infoWord, tx, x0, y, z, f, edge);

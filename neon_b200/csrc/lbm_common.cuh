@@ -97,6 +97,7 @@ struct DenseArgs
     int32_t wpr;          // summary words per row
     int32_t zm0;          // first memory plane of the view
     int32_t fold, skip;   // view planes >= fold are shifted by skip (BOUNDARY view: two slabs)
+    int32_t lprLog2;      // direct kernel: log2 of the lanes a warp spends on one row (32 = whole-row warps)
     int32_t flagsAlways;  // direct kernel: fetch the flag words with the populations instead of consulting the row summary first
     double  omega;
 };
@@ -191,15 +192,24 @@ __device__ __forceinline__ double ldPredCoherent1(const double* p, bool pred, do
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
     return keep;
 }
+// flag words of VEC cells; pred == false yields "undefined" cells (never updated)
 template <int VEC>
-__device__ __forceinline__ void ldFlags(const uint32_t* p, uint32_t (&v)[VEC])
+__device__ __forceinline__ void ldFlags(const uint32_t* p, bool pred, uint32_t (&v)[VEC])
 {
+    constexpr uint32_t U = (uint32_t)NLBM_UNDEFINED << NLBM_FLAG_CLASS_SHIFT;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        v[i] = U;
     if constexpr (VEC == 4)
-        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p));
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\n@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n}\n"
+                     : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3])
+                     : "l"(p), "r"((uint32_t)pred));
     else if constexpr (VEC == 2)
-        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];\n" : "=r"(v[0]), "=r"(v[1]) : "l"(p));
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\n@q ld.global.nc.v2.u32 {%0, %1}, [%2];\n}\n"
+                     : "+r"(v[0]), "+r"(v[1])
+                     : "l"(p), "r"((uint32_t)pred));
     else
-        asm volatile("ld.global.nc.u32 %0, [%1];\n" : "=r"(v[0]) : "l"(p));
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.u32 %0, [%1];\n}\n" : "+r"(v[0]) : "l"(p), "r"((uint32_t)pred));
 }
 __device__ __forceinline__ uint2 ldPredU2(const uint2* p)
 {

@@ -16,6 +16,7 @@ struct DenseArgs;
 struct StepLaunch
 {
     int         nzView, vec, rowsLog2;
+    int         rpwSel;  // direct kernel: rows per warp selector (0 default, else log2(rows) + 1)
     const void* tmapA;  // CUtensorMap over pop_in with box (TX, TY), or nullptr
     const void* tmapB;  // same with box (TX + 16 B, TY): populations with c_x != 0
     const void* tmapF;  // 3-D map over the flag words, box (TX, TY, 1)

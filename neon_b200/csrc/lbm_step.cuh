@@ -7,7 +7,7 @@
 // apps/lbmMultiRes/{stream.h:5-49, collide.h:286-354, util.h:47-62}.
 //
 // Design (B200, HBM-bound: every population element is read once and written once per iteration):
-//  * SoA planes with a 512-byte aligned row pitch; one warp owns 32*VEC consecutive cells of one row;
+//  * SoA planes with a 512-byte aligned row pitch; one warp owns a tile of RPW rows x (32/RPW)*VEC consecutive cells;
 //    every population row is fetched with ONE aligned 16-byte load per thread.  The +-1 x shift of the
 //    populations with c_x != 0 is served inside the warp by a shuffle; only the two edge lanes issue a
 //    4/8-byte load, which hits a sector the neighbouring warp streams anyway.
@@ -210,28 +210,28 @@ struct CollideD3Q27Fast
 // cannot supply); shiftOne then realises the x shift in registers.
 template <class L, int q, typename T, int VEC>
 __device__ __forceinline__ void loadOne(const T* __restrict__ cell0, const DenseArgs& a, const int x0, const int y, const int zm,
-                                        const int lane, T (&v)[VEC], T& edge)
+                                        const int tx, const int lpr, const bool rowOk, T (&v)[VEC], T& edge)
 {
     constexpr int cx = L::c(q, 0), cy = L::c(q, 1), cz = L::c(q, 2);
     const int     ys = y - cy, zs = zm - cz;
-    // warp-uniform: rows outside the allocation are never dereferenced (an enclosed geometry has no bulk cell there)
-    const bool ok = (cy == 0 || (unsigned)ys < (unsigned)a.ny) && (cz == 0 || (unsigned)zs < (unsigned)a.nzm);
+    // rows outside the allocation are never dereferenced (an enclosed geometry has no bulk cell there)
+    const bool ok = rowOk && (cy == 0 || (unsigned)ys < (unsigned)a.ny) && (cz == 0 || (unsigned)zs < (unsigned)a.nzm);
     const T*   p = cell0 + (q * a.pitch_q - cz * a.pitch_z - (int64_t)cy * a.pitch_y);
     ldPred(p, ok, v);
     edge = T(0);
     if constexpr (cx == 1)
-        edge = ldPred1(p - 1, lane == 0 && ok && x0 > 0);
+        edge = ldPred1(p - 1, tx == 0 && ok && x0 > 0);
     else if constexpr (cx == -1)
-        edge = ldPred1(p + VEC, lane == 31 && ok && x0 + VEC < a.pitch_y);
+        edge = ldPred1(p + VEC, tx == lpr - 1 && ok && x0 + VEC < a.pitch_y);
 }
 
 template <class L, int q, typename T, int VEC>
-__device__ __forceinline__ void shiftOne(const int lane, T (&v)[VEC], const T edge)
+__device__ __forceinline__ void shiftOne(const int tx, const int lpr, T (&v)[VEC], const T edge)
 {
     constexpr int cx = L::c(q, 0);
     if constexpr (cx == 1) {
         T e = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
-        if (lane == 0)
+        if (tx == 0)
             e = edge;
 #pragma unroll
         for (int i = VEC - 1; i > 0; --i)
@@ -239,7 +239,7 @@ __device__ __forceinline__ void shiftOne(const int lane, T (&v)[VEC], const T ed
         v[0] = e;
     } else if constexpr (cx == -1) {
         T e = __shfl_down_sync(0xffffffffu, v[0], 1);
-        if (lane == 31)
+        if (tx == lpr - 1)
             e = edge;
 #pragma unroll
         for (int i = 0; i < VEC - 1; ++i)
@@ -250,14 +250,16 @@ __device__ __forceinline__ void shiftOne(const int lane, T (&v)[VEC], const T ed
 
 template <class L, typename T, int VEC, int... Qs>
 __device__ __forceinline__ void loadAll(std::integer_sequence<int, Qs...>, const T* __restrict__ cell0, const DenseArgs& a,
-                                        const int x0, const int y, const int zm, const int lane, T (&f)[L::Q][VEC], T (&edge)[L::Q])
+                                        const int x0, const int y, const int zm, const int tx, const int lpr, const bool rowOk,
+                                        T (&f)[L::Q][VEC], T (&edge)[L::Q])
 {
-    (loadOne<L, Qs, T, VEC>(cell0, a, x0, y, zm, lane, f[Qs], edge[Qs]), ...);
+    (loadOne<L, Qs, T, VEC>(cell0, a, x0, y, zm, tx, lpr, rowOk, f[Qs], edge[Qs]), ...);
 }
 template <class L, typename T, int VEC, int... Qs>
-__device__ __forceinline__ void shiftAll(std::integer_sequence<int, Qs...>, const int lane, T (&f)[L::Q][VEC], const T (&edge)[L::Q])
+__device__ __forceinline__ void shiftAll(std::integer_sequence<int, Qs...>, const int tx, const int lpr, T (&f)[L::Q][VEC],
+                                         const T (&edge)[L::Q])
 {
-    (shiftOne<L, Qs, T, VEC>(lane, f[Qs], edge[Qs]), ...);
+    (shiftOne<L, Qs, T, VEC>(tx, lpr, f[Qs], edge[Qs]), ...);
 }
 
 // ---------------------------------------------------------------- wall fix-up (half-way bounce-back, moving walls)
@@ -413,17 +415,22 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
+    // a warp covers RPW = 32 / LPR consecutive rows x (LPR * VEC) consecutive cells: the narrower the x extent, the fewer
+    // warps touch the x walls and pay the wall round trip (summary-first mode keeps whole-row warps, LPR = 32)
     const int lane = threadIdx.x;
+    const int lpr = 1 << a.lprLog2, tx = lane & (lpr - 1), r = lane >> a.lprLog2;
     const int seg = blockIdx.x * blockDim.y + threadIdx.y;
-    const int y = blockIdx.y * blockDim.z + threadIdx.z;
+    const int yw = (blockIdx.y * blockDim.z + threadIdx.z) * (32 >> a.lprLog2);
+    const int y = yw + r;
     const int vz = blockIdx.z;
     const int zm = a.zm0 + vz + (vz >= a.fold ? a.skip : 0);
-    const int xw = seg * (32 * VEC);
-    if (xw >= a.nx || y >= a.ny)
+    const int xw = seg * (lpr * VEC);
+    if (xw >= a.nx || yw >= a.ny)
         return;  // warp-uniform
+    const bool    rowOk = y < a.ny;
     const int64_t row = (int64_t)zm * a.ny + y;
-    const int     chunk0 = seg * VEC;  // the warp's VEC chunks lie in one summary word (VEC divides 32)
-    const int     x0 = xw + lane * VEC;
+    const int     chunk0 = seg * VEC;  // summary-first mode: the warp's VEC chunks lie in one summary word (VEC divides 32)
+    const int     x0 = xw + tx * VEC;
     const int64_t cellOff = (int64_t)zm * a.pitch_z + (int64_t)y * a.pitch_y + x0;
     const T*      cell0 = reinterpret_cast<const T*>(a.in) + cellOff;
 
@@ -431,11 +438,11 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     uint2    s = make_uint2(0u, 0u);
     uint32_t fl[VEC];
     if (a.flagsAlways)
-        ldFlags<VEC>(a.flags + cellOff, fl);
+        ldFlags<VEC>(a.flags + cellOff, rowOk, fl);
     else
         s = ldPredU2(a.summary + row * a.wpr + (chunk0 >> 5));
     T f[Q][VEC], edge[Q];
-    loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, lane, f, edge);
+    loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, tx, lpr, rowOk, f, edge);
 
     bool special;
     if (a.flagsAlways) {
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
         const uint32_t wspec = (s.x >> (chunk0 & 31)) & cm;
         special = (wspec >> ((lane * VEC) >> 5)) & 1u;
         if (special) {
-            ldFlags<VEC>(a.flags + cellOff, fl);
+            ldFlags<VEC>(a.flags + cellOff, true, fl);
         } else {
 #pragma unroll
             for (int i = 0; i < VEC; ++i)
@@ -464,18 +471,42 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
         }
     }
 
-    shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, lane, f, edge);
+    shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, tx, lpr, f, edge);
 
     finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
 }
 
 // =============================================================== host launcher
 template <class COL, typename T, int VEC>
-inline cudaError_t launchStepVec(const DenseArgs& a, int nzView, int rowsLog2, cudaStream_t st)
+inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
 {
-    const int segs = (a.nx + 32 * VEC - 1) / (32 * VEC);
-    // default: the 8 warps of a block take the same x segment of 8 consecutive rows, so that the warps which need the
-    // extra round trip of wall handling (segments touching a wall) share blocks and do not hold back plain ones
+    // warp tile: RPW rows x (32 / RPW * VEC) cells.  Measured on B200 (profiles/r01k): whole-row warps are best when rows
+    // are long (the SoA planes like long contiguous runs); on short rows every whole-row warp touches an x wall and pays
+    // the wall round trip, so the tile narrows until a row has at least four pieces — never below 128 bytes per piece.
+    // Whole-row warps when the row summary gates the flag loads.
+    int lprLog2 = 5;
+    if (a.flagsAlways) {
+        int want = 32;
+        if (rpwSel > 0) {
+            want = 32 >> (rpwSel - 1);
+        } else {
+            const int minLanes = 128 / (VEC * (int)sizeof(T)) < 2 ? 2 : 128 / (VEC * (int)sizeof(T));
+            while (want > minLanes && want * VEC * 4 > a.nx)
+                want >>= 1;
+        }
+        if (want > 32)
+            want = 32;
+        if (want < 2)
+            want = 2;
+        lprLog2 = 0;
+        while ((1 << lprLog2) < want)
+            ++lprLog2;
+    }
+    a.lprLog2 = lprLog2;
+    const int rpw = 32 >> lprLog2;
+    const int segs = (a.nx + (VEC << lprLog2) - 1) / (VEC << lprLog2);
+    // the 8 warps of a block stack in y by default, so that the warps which need the extra round trip of wall handling
+    // (segments touching an x wall) share blocks and do not hold back plain ones
     int warps = kStepThreads / 32;
     int sx = 1;
     int rows = warps / sx;
@@ -486,15 +517,17 @@ inline cudaError_t launchStepVec(const DenseArgs& a, int nzView, int rowsLog2, c
         sx = warps / rows;
     }
     dim3 block(32, sx, rows);
-    dim3 grid((segs + sx - 1) / sx, (a.ny + rows - 1) / rows, nzView);
+    dim3 grid((segs + sx - 1) / sx, (a.ny + rows * rpw - 1) / (rows * rpw), nzView);
     if (nzView <= 0)
         return cudaSuccess;
+    if (grid.y > 65535)
+        return cudaErrorInvalidConfiguration;
     k_dense_step<COL, T, VEC><<<grid, block, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 template <class COL, typename T>
-inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsLog2, cudaStream_t st)
+inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
 {
     constexpr int maxVec = 16 / (int)sizeof(T);
     if (vec <= 0 || vec > maxVec) {
@@ -507,11 +540,11 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
         vec >>= 1;
     if constexpr (maxVec >= 4) {
         if (vec == 4)
-            return launchStepVec<COL, T, 4>(a, nzView, rowsLog2, st);
+            return launchStepVec<COL, T, 4>(a, nzView, rowsLog2, rpwSel, st);
     }
     if (vec >= 2)
-        return launchStepVec<COL, T, 2>(a, nzView, rowsLog2, st);
-    return launchStepVec<COL, T, 1>(a, nzView, rowsLog2, st);
+        return launchStepVec<COL, T, 2>(a, nzView, rowsLog2, rpwSel, st);
+    return launchStepVec<COL, T, 1>(a, nzView, rowsLog2, rpwSel, st);
 }
 
 }  // namespace nlbm

@@ -10,7 +10,7 @@ cudaError_t go(const DenseArgs& a, const StepLaunch& l, cudaStream_t st)
 {
     if (l.tmapA)
         return launchStepTma<COL, T>(a, l.nzView, l.tmapA, l.tmapB, l.tmapF, l.groups, l.numSms, st);
-    return launchStep<COL, T>(a, l.nzView, l.vec, l.rowsLog2, st);
+    return launchStep<COL, T>(a, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
 }
 }  // namespace
 

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--workload", default="")
     ap.add_argument("--arith", default="fast", choices=["fast", "reference"])
     ap.add_argument("--occ", default="standard", choices=["none", "standard"])
-    ap.add_argument("--transport", default="auto", choices=["auto", "packed", "views", "ipc"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "packed", "views", "ipc", "fused"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "tma"])
     ap.add_argument("--vec", type=int, default=0)
     ap.add_argument("--tma-l2promo", type=int, default=0)
@@ -271,8 +271,8 @@ def main():
     dn, up = grid.neighbours()
     nnb = (dn is not None) + (up is not None)
     # halo per neighbour: ipc = push + signal + wait kernels, packed = pack + unpack kernels (+ NCCL's own), views = NCCL only
-    per_nb = {"auto": 3, "ipc": 3, "packed": 2, "views": 0}[args.transport]
-    launches_step = 1 if world == 1 else ((2 if occ != nb.Occ.none else 1) + per_nb * nnb)
+    per_nb = {"auto": 3, "ipc": 3, "packed": 2, "views": 0, "fused": 1}[args.transport]
+    launches_step = 1 if world == 1 else ((1 if args.transport == "fused" else (2 if occ != nb.Occ.none else 1)) + per_nb * nnb)
 
     # --- roofline of the dominant kernel (k_dense_step): algorithmic bytes / measured launch duration ------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -158,6 +158,28 @@ int nlbm_d3q19_f32c64_dense_step(const nlbm_dense_desc* d, double omega, int dat
 int nlbm_d3q27_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
 int nlbm_d3q27_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream);
 
+/* ---- fused iteration + halo update (one kernel does both, over peer memory) --------------------------------------
+ * The reference runs, per iteration and device, [host sync -> 19 peer copies per direction -> kernel] (Occ::none) or the
+ * INTERNAL kernel next to [sync -> copies -> BOUNDARY kernel] (Occ::standard; multiGpuGraph.cpp:120-143,304-352).  Here ONE
+ * launch updates the whole partition, takes its two z-boundary planes first, stores the populations that cross each face
+ * (D3Q19: 5, D3Q27: 9) straight into the neighbour's ghost plane of the field that corresponds to pop_out (a peer / CUDA-IPC
+ * mapping; NVLink stores), and the last warp of a plane publishes `value` in the neighbour's flag word.  The caller
+ * enqueues nlbm_flag_wait(my flag >= value of the previous iteration) before the next launch: the ghost planes an
+ * iteration reads were written during the neighbours' previous iteration, so the exchange hides behind the interior.
+ * The ghost planes of pop_in must be current at the first call (one ordinary halo update).  nz_local >= 2.
+ * kind: 0 D3Q19 f32, 1 D3Q19 f64, 2 D3Q19 f32 store / f64 compute, 3 D3Q27 f32, 4 D3Q27 f64.                            */
+typedef struct nlbm_peer_desc {
+    void*     down_field;    /* lower neighbour's field corresponding to pop_out (device pointer valid HERE), or NULL */
+    void*     up_field;      /* upper neighbour's, or NULL */
+    int32_t   down_nz_local; /* slab heights of the neighbours (they fix where their ghost planes are) */
+    int32_t   up_nz_local;
+    uint32_t* down_flag;     /* word in the lower neighbour's memory: receives `value` when my plane 0 is in its upper ghost */
+    uint32_t* up_flag;       /* word in the upper neighbour's memory: receives `value` when my top plane is in its lower ghost */
+    uint32_t* counters;      /* 2 words of THIS device's memory, zero before the first call, owned by the caller */
+    uint32_t  value;
+} nlbm_peer_desc;
+int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream);
+
 /* LbmContainers::computeRhoAndU, LbmTools.h:384-437 (D3Q19).  rho: [zm][y][x] with the
  * descriptor's pitches; u: 3 such planes sets, pitch_q apart.                        */
 int nlbm_d3q19_f32_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream);

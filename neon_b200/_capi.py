@@ -77,6 +77,14 @@ class BlockDesc(C.Structure):
         return d
 
 
+class PeerDesc(C.Structure):
+    """struct nlbm_peer_desc"""
+    _fields_ = [
+        ("down_field", C.c_void_p), ("up_field", C.c_void_p), ("down_nz_local", C.c_int32), ("up_nz_local", C.c_int32),
+        ("down_flag", C.c_void_p), ("up_flag", C.c_void_p), ("counters", C.c_void_p), ("value", C.c_uint32),
+    ]
+
+
 _P = C.c_void_p
 _D = C.POINTER(DenseDesc)
 _B = C.POINTER(BlockDesc)
@@ -95,6 +103,7 @@ _SIGNATURES = {
     "nlbm_d3q19_f32c64_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
     "nlbm_d3q27_f32_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
     "nlbm_d3q27_f64_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_dense_step_push": (C.c_int, [C.c_int, _D, C.POINTER(PeerDesc), C.c_double, C.c_int, _P]),
     "nlbm_d3q19_f32_dense_rho_u": (C.c_int, [_D, _P, _P, _P]),
     "nlbm_d3q19_f64_dense_rho_u": (C.c_int, [_D, _P, _P, _P]),
     "nlbm_dense_halo_push": (C.c_int, [_D, _P, _D, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -129,7 +129,8 @@ int smCount()
     return sms[dev];
 }
 
-int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, double omega, int view, int opts, void* stream)
+int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, double omega, int view, int opts, void* stream,
+             const nlbm_peer_desc* peer = nullptr)
 {
     if (int rc = checkDesc(d, elemBytes, true, true, true))
         return rc;
@@ -153,6 +154,36 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.omega = omega;
     a.flagsAlways = ((opts >> 20) & 1) ? 0 : 1;
     a.lprLog2 = 5;
+    a.peerMode = 0;
+    a.nzLocal = d->nz_local;
+    a.peer[0] = a.peer[1] = nullptr;
+    a.peerOff[0] = a.peerOff[1] = a.peerPitchQ[0] = a.peerPitchQ[1] = 0;
+    a.peerFlag[0] = a.peerFlag[1] = nullptr;
+    a.counter = nullptr;
+    a.signalValue = a.warpsPerFace = 0;
+    if (peer) {
+        if (view != NLBM_VIEW_STANDARD)
+            return fail(NLBM_ERR_INVALID, "the fused step updates the whole partition");
+        if (d->z_halo != 1 || d->nz_local < 2)
+            return fail(NLBM_ERR_INVALID, "the fused step needs ghost planes and at least two local planes");
+        if (!peer->counters || ((uintptr_t)peer->counters & 3))
+            return fail(NLBM_ERR_INVALID, "counters null or misaligned");
+        if ((peer->down_field && (!peer->down_flag || peer->down_nz_local < 1)) || (peer->up_field && (!peer->up_flag || peer->up_nz_local < 1)))
+            return fail(NLBM_ERR_INVALID, "a neighbour needs its field, flag word and slab height");
+        a.peerMode = 1;
+        a.peer[0] = peer->down_field;
+        a.peer[1] = peer->up_field;
+        // my plane 0 lands in the lower neighbour's UPPER ghost plane (memory plane nz + 1), my top plane in the upper
+        // neighbour's LOWER ghost plane (memory plane 0)
+        a.peerOff[0] = (int64_t)(peer->down_nz_local + 1) * d->pitch_z;
+        a.peerOff[1] = 0;
+        a.peerPitchQ[0] = d->pitch_z * (peer->down_nz_local + 2);
+        a.peerPitchQ[1] = d->pitch_z * (peer->up_nz_local + 2);
+        a.peerFlag[0] = peer->down_flag;
+        a.peerFlag[1] = peer->up_flag;
+        a.counter = peer->counters;
+        a.signalValue = peer->value;
+    }
     // Views split at stencil radius 1 (both lattices): INTERNAL = local z in [1, nz-1), BOUNDARY = {0, nz-1}
     // (the reference's BOUNDARY span folds wrongly; this is the intended cover).
     const int r = 1, nz = d->nz_local;
@@ -182,7 +213,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     l.tmapF = nullptr;
     l.groups = (opts >> 18) & 0x3;
     l.numSms = 0;
-    const int   kernelSel = (opts >> 12) & 0xF;  // 0 auto, 1 direct loads, 2 TMA-fed persistent
+    const int   kernelSel = peer ? 1 : (opts >> 12) & 0xF;  // 0 auto, 1 direct loads, 2 TMA-fed persistent
     const int   q = (kind == nlbm::kD3Q27_F32 || kind == nlbm::kD3Q27_F64) ? 27 : 19;
     CUtensorMap tmapA, tmapB, tmapF;
     const int   promo = (opts >> 16) & 0x3;
@@ -347,6 +378,16 @@ int nlbm_d3q27_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_v
 int nlbm_d3q27_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
 {
     return stepImpl(nlbm::kD3Q27_F64, 8, d, omega, data_view, opts, stream);
+}
+
+int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream)
+{
+    if (kind < 0 || kind > 4)
+        return fail(NLBM_ERR_INVALID, "bad kind %d", kind);
+    if (!peer)
+        return fail(NLBM_ERR_INVALID, "null peer descriptor");
+    const int elem = (kind == nlbm::kD3Q19_F64 || kind == nlbm::kD3Q27_F64) ? 8 : 4;
+    return stepImpl((nlbm::StepKind)kind, elem, d, omega, NLBM_VIEW_STANDARD, opts, stream, peer);
 }
 
 int nlbm_d3q19_f32_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, void* stream)

@@ -100,6 +100,16 @@ struct DenseArgs
     int32_t lprLog2;      // direct kernel: log2 of the lanes a warp spends on one row (32 = whole-row warps)
     int32_t flagsAlways;  // direct kernel: fetch the flag words with the populations instead of consulting the row summary first
     double  omega;
+    // ---- fused face push (nlbm_dense_step_push): the kernel stores the crossing populations of its two z-boundary planes
+    // straight into the z-neighbours' ghost planes and signals them; all null / 0 for the plain step
+    int32_t   peerMode;       // 1: boundary planes first, peer stores, signalling
+    int32_t   nzLocal;        // planes of the partition (peerMode: plane order 0, nz-1, 1, 2, ...)
+    void*     peer[2];        // [0] the neighbour BELOW (receives my plane 0), [1] ABOVE (receives my plane nz-1); may be null
+    int64_t   peerOff[2];     // element offset of the ghost plane inside the neighbour's population 0
+    int64_t   peerPitchQ[2];  // the neighbour's pitch_q
+    uint32_t* peerFlag[2];    // word in the neighbour's memory that receives signalValue once the whole plane is there
+    uint32_t* counter;        // 2 words of local memory (zero between launches): warps of plane 0 / plane nz-1 that finished
+    uint32_t  signalValue, warpsPerFace;
 };
 
 // ---------------------------------------------------------------- vector access

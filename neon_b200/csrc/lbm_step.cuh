@@ -352,7 +352,8 @@ __device__ __forceinline__ void fixCell(const T* __restrict__ cell, const DenseA
 // Wall fix-ups, collision and stores of the VEC cells one thread owns (shared by the direct and the TMA kernel).
 template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5)>
 __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
-                                            const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC])
+                                            const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC],
+                                            T* __restrict__ peerDst = nullptr, const int64_t peerPitchQ = 0, const int peerDir = 0)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -402,6 +403,31 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
 #pragma unroll
     for (int q = 0; q < Q; ++q)
         stVec<T, VEC>(out0 + q * a.pitch_q, f[q]);
+    if (peerDst != nullptr) {
+        // fused halo update: the populations that cross this z face also go straight into the neighbour's ghost plane
+        // (peer memory, NVLink stores) — what nlbm_dense_halo_push would copy after the kernel
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            if (L::c(q, 2) != 0 && L::c(q, 2) == peerDir)
+                stVec<T, VEC>(peerDst + q * peerPitchQ, f[q]);
+        }
+    }
+}
+
+// All warps of a boundary plane report in (on every exit path); the last one publishes the counter the neighbour waits for.
+__device__ __forceinline__ void faceArrive(const DenseArgs& a, const int face, const int lane)
+{
+    __threadfence_system();  // my peer stores are visible system-wide before my warp counts as done
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t done = atomicAdd(a.counter + face, 1u);
+        if (done == a.warpsPerFace - 1) {
+            a.counter[face] = 0;  // ready for the next launch
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t*>(a.peerFlag[face]) = a.signalValue;
+            __threadfence_system();
+        }
+    }
 }
 
 // =============================================================== the kernel
@@ -410,7 +436,8 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
 __host__ __device__ constexpr int stepMinBlocks(int valueRegs) { return valueRegs <= 40 ? 3 : (valueRegs <= 80 ? 2 : 1); }
 
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
-template <class COL, typename T, int VEC>
+// PEER: the fused step + face push (nlbm_dense_step_push); a separate instantiation so that the plain kernel carries none of it
+template <class COL, typename T, int VEC, bool PEER>
 __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
 {
     constexpr int Q = COL::Q;
@@ -423,10 +450,18 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     const int yw = (blockIdx.y * blockDim.z + threadIdx.z) * (32 >> a.lprLog2);
     const int y = yw + r;
     const int vz = blockIdx.z;
-    const int zm = a.zm0 + vz + (vz >= a.fold ? a.skip : 0);
-    const int xw = seg * (lpr * VEC);
-    if (xw >= a.nx || yw >= a.ny)
-        return;  // warp-uniform
+    // fused face push: the two boundary planes come first (blockIdx.z 0 -> plane 0, 1 -> plane nz-1, then 1, 2, ...) so
+    // that the neighbours have their ghost planes long before they start the next iteration
+    const int  zl = PEER ? (vz == 0 ? 0 : (vz == 1 ? a.nzLocal - 1 : vz - 1)) : 0;
+    const int  zm = PEER ? a.zm0 + zl : a.zm0 + vz + (vz >= a.fold ? a.skip : 0);
+    const int  face = PEER && vz < 2 ? vz : -1;
+    const bool pushes = PEER && face >= 0 && a.peer[face] != nullptr;
+    const int  xw = seg * (lpr * VEC);
+    if (xw >= a.nx || yw >= a.ny) {  // warp-uniform
+        if (pushes)
+            faceArrive(a, face, lane);
+        return;
+    }
     const bool    rowOk = y < a.ny;
     const int64_t row = (int64_t)zm * a.ny + y;
     const int     chunk0 = seg * VEC;  // summary-first mode: the warp's VEC chunks lie in one summary word (VEC divides 32)
@@ -452,14 +487,20 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
             plain = plain && fl[i] == kPlainBulk;
             bulk = bulk || flagIsBulk(fl[i]);
         }
-        if (!__any_sync(0xffffffffu, bulk))
-            return;  // no bulk cell in this warp's segment: nothing to update
+        if (!__any_sync(0xffffffffu, bulk)) {  // no bulk cell in this warp's segment: nothing to update
+            if (pushes)
+                faceArrive(a, face, lane);
+            return;
+        }
         special = !plain;
     } else {
         const uint32_t cm = (1u << VEC) - 1u;
         const uint32_t wbulk = (s.y >> (chunk0 & 31)) & cm;
-        if (wbulk == 0)
-            return;  // no bulk cell in this warp's segment: nothing to update
+        if (wbulk == 0) {  // no bulk cell in this warp's segment: nothing to update
+            if (pushes)
+                faceArrive(a, face, lane);
+            return;
+        }
         const uint32_t wspec = (s.x >> (chunk0 & 31)) & cm;
         special = (wspec >> ((lane * VEC) >> 5)) & 1u;
         if (special) {
@@ -473,11 +514,19 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
 
     shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, tx, lpr, f, edge);
 
-    finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
+    if constexpr (PEER) {
+        const int fi = pushes ? face : 0;
+        T*        peerDst = (pushes && rowOk) ? reinterpret_cast<T*>(a.peer[fi]) + a.peerOff[fi] + (int64_t)y * a.pitch_y + x0 : nullptr;
+        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi], fi == 0 ? -1 : 1);
+        if (pushes)
+            faceArrive(a, face, lane);
+    } else {
+        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
+    }
 }
 
 // =============================================================== host launcher
-template <class COL, typename T, int VEC>
+template <class COL, typename T, int VEC, bool PEER = false>
 inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
 {
     // warp tile: RPW rows x (32 / RPW * VEC) cells.  Measured on B200 (profiles/r01k): whole-row warps are best when rows
@@ -522,7 +571,8 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
         return cudaSuccess;
     if (grid.y > 65535)
         return cudaErrorInvalidConfiguration;
-    k_dense_step<COL, T, VEC><<<grid, block, 0, st>>>(a);
+    a.warpsPerFace = grid.x * grid.y * (unsigned)warps;  // every warp launched for a plane reports in
+    k_dense_step<COL, T, VEC, PEER><<<grid, block, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -538,6 +588,12 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
     }
     while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
         vec >>= 1;
+    if (a.peerMode) {  // the fused step + face push exists for the default access width of each lattice / precision
+        constexpr int dv = (COL::Q * maxVec * (int)sizeof(T) / 4 > 80) ? maxVec / 2 : maxVec;
+        if (a.pitch_y % (32 * dv) != 0)
+            return cudaErrorInvalidConfiguration;
+        return launchStepVec<COL, T, dv, true>(a, nzView, rowsLog2, rpwSel, st);
+    }
     if constexpr (maxVec >= 4) {
         if (vec == 4)
             return launchStepVec<COL, T, 4>(a, nzView, rowsLog2, rpwSel, st);

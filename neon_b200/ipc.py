@@ -132,3 +132,78 @@ class IpcHalo:
 
     def timeouts(self) -> int:
         return int(self.err.item())
+
+
+class FusedIteration:
+    """LBM iteration whose halo update is fused into the step kernel (nlbm_dense_step_push, include/neon_lbm.h).
+
+    Per iteration and rank: [nlbm_flag_wait per neighbour] + ONE kernel.  The kernel takes the two z-boundary planes
+    first, stores their face-crossing populations straight into the neighbours' ghost planes (CUDA-IPC mappings, NVLink
+    stores) and publishes the iteration counter in the neighbours' flag words; the neighbours wait for that counter
+    before their next launch.  Compared with Skeleton + Occ::standard (INTERNAL kernel next to halo + BOUNDARY kernel,
+    libNeonSkeleton/src/skeleton/internal/multiGpuGraph.cpp:120-143) there is no view split, no copy kernel and no
+    second stream.  Hazards: RAW — iteration t reads ghost planes written during the neighbours' iteration t-1 and waits
+    for their counter t; WAR — a neighbour's ghost plane of field B is overwritten during my iteration t only after its
+    boundary planes of iteration t-1 (the last readers) reported in, which is what its counter t says.
+    """
+
+    KIND = {(19, "float32", "float32"): 0, (19, "float64", "float64"): 1, (19, "float32", "float64"): 2,
+            (27, "float32", "float32"): 3, (27, "float64", "float64"): 4}
+
+    def __init__(self, pops, flag, omega: float, lattice_q: int, compute, arith: int, opts: int):
+        import numpy as np
+        self.pop, self.flag, self.omega, self.q = pops, flag, float(omega), lattice_q
+        f = pops[0]
+        g = f.grid
+        bk = g.backend
+        if getattr(g, "kind", "dense") != "dense" or bk.world < 2 or g.nz_local < 2:
+            raise capi.NeonException("FusedIteration", capi.ERR_UNSUPPORTED,
+                                     "the fused step + halo kernel needs a z-split dense grid with >= 2 planes per rank")
+        cdt = np.dtype(compute).name if compute is not None else f.dtype.name
+        self.kind = self.KIND[(lattice_q, f.dtype.name, cdt)]
+        self.opts = int(arith) | int(opts)
+        self.t = 0
+        self.flags = torch.zeros(_FLAG_WORDS, dtype=torch.int32, device=bk.device)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=bk.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=bk.device)
+        torch.cuda.synchronize(bk.device)
+        mine = (export_ptr(pops[0].data.data_ptr()), export_ptr(pops[1].data.data_ptr()), export_ptr(self.flags.data_ptr()))
+        handles = [None] * bk.world
+        dist.all_gather_object(handles, mine, group=bk.group)
+        self.dn, self.up = g.neighbours()
+        self.peer = {}
+        for nbr in (self.dn, self.up):
+            if nbr is not None:
+                h0, h1, hf = handles[nbr]
+                self.peer[nbr] = ((import_ptr(*h0), import_ptr(*h1)), import_ptr(*hf))
+        # the ghost planes of the first input field must be current: one ordinary halo update (it also lines the ranks up)
+        from .dgrid import StencilSemantic, TransferMode
+        self._prologue = pops[0].newHaloUpdate(StencilSemantic.streaming, TransferMode.get, lattice_q, "ipc")
+        bk.barrier()
+
+    def run(self) -> None:
+        g = self.pop[0].grid
+        bk = g.backend
+        st = bk.streamHandle(0)
+        t = self.t
+        fin, fout = self.pop[t & 1], self.pop[(t + 1) & 1]
+        if t == 0:
+            self._prologue.run(0)
+        else:
+            for nbr, slot in ((self.dn, FROM_BELOW), (self.up, FROM_ABOVE)):
+                if nbr is not None:
+                    capi.call("nlbm_flag_wait", self.flags.data_ptr() + 4 * slot, t, TIMEOUT_MS, self.err.data_ptr(), st)
+        p = capi.PeerDesc()
+        if self.dn is not None:
+            fields, fl = self.peer[self.dn]
+            p.down_field, p.down_nz_local, p.down_flag = fields[(t + 1) & 1], g.sizes[self.dn], fl + 4 * FROM_ABOVE
+        if self.up is not None:
+            fields, fl = self.peer[self.up]
+            p.up_field, p.up_nz_local, p.up_flag = fields[(t + 1) & 1], g.sizes[self.up], fl + 4 * FROM_BELOW
+        p.counters, p.value = self.counters.data_ptr(), t + 1
+        d = g.desc(fin, fout, self.flag)
+        capi.call("nlbm_dense_step_push", self.kind, C.byref(d), C.byref(p), self.omega, self.opts, st)
+        self.t = t + 1
+
+    def timeouts(self) -> int:
+        return int(self.err.item()) + self._prologue.timeouts()

@@ -111,6 +111,14 @@ class LbmIteration:
         self.flag, self.omega, self.parity = flagField, omega, 0
         bk = fInField.grid.backend
         self.lbmTwoPop = []
+        self.fused = None
+        if halo_transport == "fused" and bk.world > 1:
+            # B200-first alternative to the Skeleton's OCC graph: the halo update is part of the step kernel
+            from .ipc import FusedIteration
+            self.fused = FusedIteration(self.pop, flagField, omega, lattice_q, compute, arith, opts)
+            return
+        if halo_transport == "fused":
+            halo_transport = "auto"
         for a, b in ((0, 1), (1, 0)):
             c = LbmContainers.iteration(stencilSemantic, self.pop[a], self.pop[b], flagField, omega, lattice_q, compute,
                                         arith, opts, halo_transport)
@@ -119,8 +127,17 @@ class LbmIteration:
             self.lbmTwoPop.append(sk)
 
     def run(self) -> None:
-        self.lbmTwoPop[self.parity].run()
+        if self.fused is not None:
+            self.fused.run()
+        else:
+            self.lbmTwoPop[self.parity].run()
         self.parity ^= 1
+
+    def timeouts(self) -> int:
+        """Device-side waits on a neighbour that gave up (peer-store transports); 0 when all faces arrived."""
+        if self.fused is not None:
+            return self.fused.timeouts()
+        return sum(h.timeouts() for sk in self.lbmTwoPop for h in sk.halos())
 
     def getInput(self) -> dField:
         return self.pop[self.parity]

@@ -1,9 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_dense.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/pytest.log
-: > gpurun_out/bench_var.log
-for v in "" "--workload cavity256" "--workload cavity256 --rpw 1" "--workload cavity256 --rpw 2" "--workload cavity256 --rpw 3" "--workload cavity128" "--workload cavity128 --rpw 1" "--workload cavity128 --rpw 2" "--workload cavity128 --rpw 3" \
-   "--workload cavity64" "--workload cavity64 --rpw 1" "--workload cavity64 --rpw 3" "--workload cavity1024" "--workload d3q27f64" "--workload slab1024"; do
-  echo "== $v" >> gpurun_out/bench_var.log
-  timeout 120 python bench.py --steps 50 --warmup 5 --no-e2e --no-cpu $v 2>&1 | tail -3 >> gpurun_out/bench_var.log
-done
+timeout 900 python -m pytest tests/test_gpu_multiproc.py -x -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_mp.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 tests/mgpu_check.py > gpurun_out/mgpu2.log 2>&1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 50 --warmup 5 --transport fused > gpurun_out/bench2_fused.json 2> gpurun_out/bench2_fused.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/bench2.json 2> gpurun_out/bench2.err

@@ -32,7 +32,7 @@ def main():
         cls = O.classify(1, *dim)
         mask = O.wall_mask(q, cls)
         ref = O.run(q, O.init_pop(q, cls, dt), cls, mask, omega, iters) if rank == 0 else None
-        for transport in ("packed", "views", "ipc"):
+        for transport in ("packed", "views", "ipc", "fused"):
             for occ in (nb.Occ.none, nb.Occ.standard):
                 grid = nb.dGrid(bk, dim)
                 pop0, pop1, flag = P.setup_device(grid, q, dt, P.CAVITY_SPHERE)
@@ -50,8 +50,8 @@ def main():
     grid = nb.dGrid(bk, dim)
     pop0, pop1, flag = P.setup_device(grid, 19, np.float32, P.CAVITY)
     om = nb.omega_from_re(dim[0])
-    for transport in ("packed", "ipc"):
-        halo = pop0.newHaloUpdate(nb.StencilSemantic.streaming, nb.TransferMode.get, 19, transport)
+    for transport in ("packed", "ipc", "fused"):
+        halo = pop0.newHaloUpdate(nb.StencilSemantic.streaming, nb.TransferMode.get, 19, "ipc" if transport == "fused" else transport)
         for _ in range(3):
             halo.run(0)
         bk.syncAll(); dist.barrier()
@@ -79,7 +79,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             out[f"iter_ms_{transport}_{occ.value}"] = float(ms.item())
             out[f"mlups_{transport}_{occ.value}"] = dim[0] * dim[1] * dim[2] / (float(ms.item()) * 1e3)
-            out[f"timeouts_{transport}_{occ.value}"] = sum(h.timeouts() for sk in it.lbmTwoPop for h in sk.halos())
+            out[f"timeouts_{transport}_{occ.value}"] = it.timeouts()
             dist.barrier()
     if rank == 0:
         print(json.dumps(out, indent=1), flush=True)

@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, results):
+def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, results, transport="ipc"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -38,11 +38,11 @@ def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, result
         grid = nb.dGrid(bk, dim) if kind == "dGrid" else nb.bGrid(bk, dim)
         pop0, pop1, flag = P.setup_device(grid, q, dtype, P.CAVITY_SPHERE)
         it = nb.LbmIteration(nb.StencilSemantic.streaming, getattr(nb.Occ, occ_name), nb.TransferMode.get, pop0, pop1, flag, 1.25,
-                             lattice_q=q, arith=nb.ARITH_REFERENCE, halo_transport="ipc")
+                             lattice_q=q, arith=nb.ARITH_REFERENCE, halo_transport=transport)
         for _ in range(iters):
             it.run()
         bk.syncAll()
-        timeouts = sum(h.timeouts() for sk in it.lbmTwoPop for h in sk.halos())
+        timeouts = it.timeouts()
         out = it.getInput().gather()
         cls, mask = flag.gather()
         if rank == 0:
@@ -68,4 +68,23 @@ def test_ipc_halo_across_processes(oracle, q, dtype, world, occ, kind):
     ref = oracle.run(q, oracle.init_pop(q, cls, np.dtype(dtype)), cls, mask, 1.25, iters)
     assert results["timeouts"] == 0
     assert np.array_equal(results["mask"], mask)
+    assert np.array_equal(results["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.parametrize("q,dtype,world", [(19, "float32", 2), (19, "float32", 3), (27, "float64", 2)])
+def test_fused_step_and_halo_kernel_across_processes(oracle, q, dtype, world):
+    """nlbm_dense_step_push: ONE kernel per iteration updates the partition and stores the face-crossing populations of its
+    boundary planes into the neighbours' ghost planes (peer memory), ordered by device-side counters.  Same bits as the
+    single-partition oracle."""
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    dim, iters = (36, 20, 23), 9
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), q, dtype, dim, iters, "none", "dGrid", results, "fused"), nprocs=world, join=True)
+    nx, ny, nz = dim
+    cls = oracle.classify(1, nx, ny, nz)
+    mask = oracle.wall_mask(q, cls)
+    ref = oracle.run(q, oracle.init_pop(q, cls, np.dtype(dtype)), cls, mask, 1.25, iters)
+    assert results["timeouts"] == 0
     assert np.array_equal(results["pop"].view(np.uint8), ref.view(np.uint8))

@@ -311,45 +311,59 @@ def main():
                 "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0}
 
     # --- e2e: host buffers -> device -> K iterations -> host ----------------------------------------------------------
+    # Every rank holds the host mirror of ITS slab (plus the in-box ghost planes), as one process per GPU implies.
     e2e = None
     if not args.no_e2e and not is_block:
         del it
+        if world > 1:  # unmap the neighbours' fields before their owners free them
+            from neon_b200 import ipc
+            barrier()
+            ipc.close_all()
+            barrier()
         pop0.data = pop1.data = None
         torch.cuda.empty_cache()
-        nzl, z0 = grid.nz_local, grid.z_origin
-        # this rank's share of the global host arrays (the public API takes global arrays; build only what is used)
-        cls = P.host_classes(P.CAVITY, dim)
-        pop_h = torch.empty((q, dim[2], dim[1], dim[0]), dtype=torch.float32 if dtype.itemsize == 4 else torch.float64,
-                            pin_memory=(world == 1)) if world == 1 else None
-        if world == 1:
-            pop_np = pop_h.numpy()
-            full = P.host_populations(q, cls[:3], dtype)  # pattern of three planes: bottom wall, interior, (reused)
-            for k in range(q):
-                pop_np[k, 0] = full[k, 0]
-                pop_np[k, 1:dim[2] - 1] = full[k, 1]
-                pop_np[k, dim[2] - 1] = full[k, 0]
-            out_h = torch.empty((q, nzl, dim[1], dim[0]), dtype=pop_h.dtype, pin_memory=True)
-            f0, f1 = grid.newField("pop0", q, dtype), grid.newField("pop1", q, dtype)
-            fl = grid.newFlagField("flag", like=f0)
-            barrier()
-            w0 = time.perf_counter()
-            fl.setClasses(cls)
-            f0.updateDeviceData(pop_h)
-            f1.updateDeviceData(pop_h)
-            fl.computeWallNghMask(q)
-            it2 = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, f0, f1, fl, omega, lattice_q=q, arith=arith,
-                                  opts=opts)
-            for _ in range(args.steps):
-                it2.run()
-            it2.getInput().updateHostDataInto(out_h)
-            bk.syncAll()
-            w1 = time.perf_counter()
-            h2d = 2 * pop_h.numel() * dtype.itemsize + cls.size * 4
-            d2h = out_h.numel() * dtype.itemsize
-            e2e = {"value": cells * args.steps / ((w1 - w0) * 1e6), "unit": "MLUPS", "h2d_bytes_per_step": h2d / args.steps,
-                   "d2h_bytes_per_step": d2h / args.steps, "seconds": w1 - w0, "steps": args.steps,
-                   "note": "whole job through the host API: pinned host populations+classes -> updateDeviceData -> wall mask -> "
-                           "K iterations -> updateHostData of the result field; bytes are job totals / K"}
+        nx, ny, nz = dim
+        nzl, z0, zh = grid.nz_local, grid.z_origin, grid.z_halo
+        lo, hi = max(0, z0 - zh), min(nz, z0 + nzl + zh)  # global planes this rank uploads
+        cls3 = P.host_classes(P.CAVITY, (nx, ny, 3))  # plane 0: z-wall, plane 1: interior
+        pop3 = P.host_populations(q, cls3, dtype)
+        tdt = torch.float32 if dtype.itemsize == 4 else torch.float64
+        pop_h = torch.empty((q, hi - lo, ny, nx), dtype=tdt, pin_memory=True)
+        pop_np = pop_h.numpy()
+        cls = np.empty((hi - lo, ny, nx), np.int32)
+        for gz in range(lo, hi):
+            w = 0 if gz in (0, nz - 1) else 1
+            cls[gz - lo] = cls3[w]
+            pop_np[:, gz - lo] = pop3[:, w]
+        out_h = pop_h[:, z0 - lo:z0 - lo + nzl]  # the result lands in the same pinned buffer (uploads are done by then)
+        f0, f1 = grid.newField("pop0", q, dtype), grid.newField("pop1", q, dtype)
+        fl = grid.newFlagField("flag", like=f0)
+        barrier()
+        w0 = time.perf_counter()
+        fl.setClasses(cls, host_z0=lo)
+        f0.updateDeviceData(pop_h, host_z0=lo)
+        f1.updateDeviceData(pop_h, host_z0=lo)
+        fl.computeWallNghMask(q)
+        it2 = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, f0, f1, fl, omega, lattice_q=q, arith=arith,
+                              opts=opts, halo_transport=args.transport)
+        for _ in range(args.steps):
+            it2.run()
+        it2.getInput().updateHostDataInto(out_h)
+        barrier()
+        w1 = time.perf_counter()
+        secs = torch.tensor([w1 - w0], dtype=torch.float64, device=bk.device)
+        traffic_hd = torch.tensor([2.0 * pop_h.numel() * dtype.itemsize + cls.size * 4, float(out_h.numel() * dtype.itemsize)],
+                                  dtype=torch.float64, device=bk.device)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+            dist.all_reduce(traffic_hd, op=dist.ReduceOp.SUM)
+        secs = float(secs.item())
+        h2d, d2h = float(traffic_hd[0].item()), float(traffic_hd[1].item())
+        e2e = {"value": cells * args.steps / (secs * 1e6), "unit": "MLUPS", "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": secs, "steps": args.steps,
+               "note": "whole job through the host API, max over ranks: pinned host populations+classes of every rank's slab -> "
+                       "updateDeviceData -> wall mask -> K iterations (with halo updates) -> updateHostData of the result field; "
+                       "an LBM iteration has no per-step host input, so bytes are job totals over all ranks / K"}
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:

@@ -152,19 +152,22 @@ class dField(_FieldBase):
         self._halo_buffers = {}
 
     # --- host <-> device (FieldBase::updateDeviceData / updateHostData) -------------------------------------------
-    def updateDeviceData(self, host, stream_idx: int = 0) -> None:
+    def updateDeviceData(self, host, stream_idx: int = 0, host_z0: int = 0) -> None:
         """``host`` is the GLOBAL field [cardinality, nz, ny, nx] (numpy array or — for asynchronous copies — a pinned
         torch tensor); this rank takes its slab and, where they lie inside the box, its ghost planes.  Enqueued on the
-        main stream like FieldBase::updateDeviceData(streamIdx)."""
+        main stream like FieldBase::updateDeviceData(streamIdx).  A rank that holds only its own part of the host
+        mirror (one process per GPU) passes the planes [host_z0, host_z0 + host.shape[1]) of the global field; they
+        must cover its slab and in-box ghost planes."""
         g = self.grid
         nx, ny, nz = g.dim
-        assert tuple(host.shape) == (self.cardinality, nz, ny, nx), host.shape
         planes = self._global_planes()
         zm0, gz0 = planes[0]
         n = len(planes)
+        assert tuple(host.shape[2:]) == (ny, nx) and host.shape[0] == self.cardinality, host.shape
+        assert host_z0 <= gz0 and gz0 + n <= host_z0 + host.shape[1] <= nz, (host_z0, host.shape, gz0, n)
         if isinstance(host, np.ndarray):
             host = torch.from_numpy(np.ascontiguousarray(host, dtype=self.dtype))
-        src = host[:, gz0:gz0 + n]
+        src = host[:, gz0 - host_z0:gz0 - host_z0 + n]
         if self.pitch_y == nx:  # rows are dense: one contiguous copy per component
             for q in range(self.cardinality):
                 self.view4[q, zm0:zm0 + n].copy_(src[q], non_blocking=True)
@@ -220,15 +223,16 @@ class FlagField(_FieldBase):
     def _d(self) -> capi.DenseDesc:
         return self.grid.desc(None, None, self)
 
-    def setClasses(self, cls_global: np.ndarray, stream_idx: int = 0) -> None:
+    def setClasses(self, cls_global: np.ndarray, stream_idx: int = 0, host_z0: int = 0) -> None:
         """Upload cell classes [nz, ny, nx] (0 bounceBack, 1 movingWall, 2 bulk); padding and planes outside the box
-        become ``undefined``; wall bits are cleared."""
+        become ``undefined``; wall bits are cleared.  ``host_z0``: global z of the first plane of ``cls_global`` when
+        the caller holds only the planes this rank needs (slab + in-box ghost planes)."""
         g = self.grid
         nx, ny, nz = g.dim
-        assert cls_global.shape == (nz, ny, nx)
+        assert cls_global.shape[1:] == (ny, nx) and host_z0 + cls_global.shape[0] <= nz, cls_global.shape
         host = np.full((g.nzm, ny, self.pitch_y), capi.UNDEFINED << capi.FLAG_CLASS_SHIFT, np.uint32)
         for zm, gz in self._global_planes():
-            host[zm, :, :nx] = cls_global[gz].astype(np.uint32) << capi.FLAG_CLASS_SHIFT
+            host[zm, :, :nx] = cls_global[gz - host_z0].astype(np.uint32) << capi.FLAG_CLASS_SHIFT
         self.cells.copy_(torch.from_numpy(host.view(np.int32)))
         if g.backend.runtime == Runtime.stream:
             capi.call("nlbm_dense_flags_commit", C.byref(self._d()), g.backend.streamHandle(stream_idx))

@@ -48,6 +48,14 @@ def import_ptr(handle: bytes, offset: int) -> int:
     return _imported[handle] + offset
 
 
+def close_all() -> None:
+    """Unmaps every neighbour allocation this process imported.  Collective in spirit: call it on every rank (between
+    barriers) BEFORE the exporting ranks free the fields, and drop the iterations/halo updates that used the mappings."""
+    for base in _imported.values():
+        capi.call("nlbm_ipc_close", C.c_void_p(base))
+    _imported.clear()
+
+
 class IpcHalo:
     def __init__(self, halo):
         self.halo = halo

@@ -1,7 +1,9 @@
 // TEST INFRASTRUCTURE — not part of the product path.
 //
 // Driver for the UNMODIFIED reference (Autodesk/Neon v0.3.3) LBM hot path on
-// its CPU/OpenMP backend.  This file is our own code; it is compiled against
+// its CPU/OpenMP backend (default) or, with --device gpu, on its own CUDA
+// backend (generic lambda kernel compiled for sm_100: the reference's GPU
+// number on the same B200).  This file is our own code; it is compiled against
 // the reference headers and sources where they lie under /root/reference (see
 // oracle/Makefile.ref) and only into oracle/_ref/.  It exists because the
 // stock benchmark never dumps populations
@@ -50,6 +52,7 @@ struct Args
     bool        isDouble = false;
     std::string grid = "dGrid";
     std::string dump;
+    std::string device = "cpu";  // "gpu": the reference's own CUDA backend (Neon::Runtime::stream), devices 0..nDev-1
     double      Re = 100., ulb = 0.04;
 };
 
@@ -74,7 +77,12 @@ static int runCase(const Args& a)
     using PopulationField = typename Grid::template Field<FP, Lattice::Q>;
 
     std::vector<int> devs(a.nDev, 0);
-    Neon::Backend    bk(devs, Neon::Runtime::openmp);
+    const bool       onGpu = a.device == "gpu";
+    if (onGpu) {
+        for (int i = 0; i < a.nDev; ++i)
+            devs[i] = i;
+    }
+    Neon::Backend bk(devs, onGpu ? Neon::Runtime::stream : Neon::Runtime::openmp);
     Lattice          lattice(bk);
     Neon::index_3d   dim(a.nx, a.ny, a.nz);
 
@@ -160,8 +168,9 @@ static int runCase(const Args& a)
         const int    timed = a.iters - warm;
         std::printf(
             "{\"ref_bench\": true, \"grid\": \"%s\", \"fp\": \"%s\", \"nx\": %d, \"ny\": %d, \"nz\": %d, \"timed_iters\": %d, "
-            "\"elapsed_us\": %.1f, \"mlups\": %.6f, \"ndev\": %d}\n",
-            a.grid.c_str(), a.isDouble ? "double" : "float", a.nx, a.ny, a.nz, timed, us, cells * timed / us, a.nDev);
+            "\"elapsed_us\": %.1f, \"mlups\": %.6f, \"ndev\": %d, \"device\": \"%s\"}\n",
+            a.grid.c_str(), a.isDouble ? "double" : "float", a.nx, a.ny, a.nz, timed, us, cells * timed / us, a.nDev,
+            a.device.c_str());
     }
 
     if (!a.dump.empty()) {
@@ -229,6 +238,8 @@ int main(int argc, char** argv)
             a.grid = next();
         } else if (k == "--dump") {
             a.dump = next();
+        } else if (k == "--device") {
+            a.device = next();
         } else {
             std::fprintf(stderr, "unknown arg %s\n", k.c_str());
             return 1;

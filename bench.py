@@ -175,6 +175,25 @@ def cpu_reference(n: int, iters: int, warm: int, fp: str = "float"):
             "threads_available": os.cpu_count()}
 
 
+def reference_gpu_backend(n: int = 256, iters: int = 60, warm: int = 10):
+    """The UNMODIFIED reference on ITS OWN CUDA backend (generic lambda kernel, nvcc -arch=sm_100) on this GPU — the
+    reference GPU number BASELINE.md §4.3 asks for.  Reported next to the bench line, never part of any timed region."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_lbm")
+    if not os.path.exists(ref):
+        return None
+    try:
+        out = subprocess.run([ref, "--device", "gpu", "--n", str(n), "--iters", str(iters), "--bench", str(warm), "--fp", "float",
+                              "--grid", "dGrid"], capture_output=True, text=True, timeout=300, cwd="/tmp")
+        for line in out.stdout.splitlines():
+            if line.startswith("{") and "ref_bench" in line:
+                r = json.loads(line)
+                return {"value": r["mlups"], "unit": "MLUPS", "kind": "reference CUDA backend (Neon v0.3.3, unmodified, sm_100)",
+                        "sample": f"lid-driven cavity D3Q19 fp32 {n}^3 dGrid, {warm}+{iters - warm} iterations, 1 GPU"}
+    except (OSError, subprocess.SubprocessError, ValueError):
+        pass
+    return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,9 +384,10 @@ def main():
                        "updateDeviceData -> wall mask -> K iterations (with halo updates) -> updateHostData of the result field; "
                        "an LBM iteration has no per-step host input, so bytes are job totals over all ranks / K"}
 
-    cpu = None
+    cpu = ref_gpu = None
     if rank == 0 and not args.no_cpu and world == 1:
         cpu = cpu_reference(args.cpu_n, args.cpu_iters + 1, 1)
+        ref_gpu = reference_gpu_backend()
 
     if rank == 0:
         line = {"metric": f"LBM MLUPS (D3Q{q} {'fp32' if dtype.itemsize == 4 else 'fp64'})", "value": mlups, "unit": "MLUPS",
@@ -377,7 +397,7 @@ def main():
                            "occ": args.occ if world > 1 else "n/a (1 partition)", "halo_transport": args.transport if world > 1 else "n/a",
                            "l2": "inputs exceed L2 (two population fields of %.1f GB per GPU)" % (q * cells_rank * dtype.itemsize / 1e9),
                            "partition": (f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes") if world > 1 else "single partition"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_step * args.steps, "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "gpu_launches": launches_step * args.steps, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -160,7 +160,15 @@ class dGrid
         if (detail::sameOffsets(mS->stencil.points(), d3q19, 19)) {
             return 19;
         }
-        return mS->stencil.nPoints() == 27 ? 27 : 0;
+        /* D3Q27 of apps/lbmMultiRes/lattice.h:15-77: x slowest, then y, then z, each in the order 0, -1, +1 */
+        int       d3q27[27][3];
+        const int order[3] = {0, -1, 1};
+        for (int k = 0; k < 27; ++k) {
+            d3q27[k][0] = order[k / 9];
+            d3q27[k][1] = order[(k / 3) % 3];
+            d3q27[k][2] = order[k % 3];
+        }
+        return detail::sameOffsets(mS->stencil.points(), d3q27, 27) ? 27 : 0;
     }
 
     /* partition descriptor without pointers */

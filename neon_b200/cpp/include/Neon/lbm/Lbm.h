@@ -1,0 +1,303 @@
+// Lbm.h — the LBM hot path behind the names the reference benchmark uses.
+//
+//   CellType                        benchmarks/lbm-lid-driven-cavity-flow/src/CellType.h:1-40
+//   D3Q19Template                   src/D3Q19.h:7-175 (c_vect :23-44, t_vect :112-132)
+//   D3Q27Template                   apps/lbmMultiRes/lattice.h:15-77 (rest population first)
+//   LbmContainers::iteration        src/LbmTools.h:285-325  -> nlbm_d3q{19,27}_*_dense_step
+//   LbmContainers::computeWallNghMask  LbmTools.h:344-376   -> nlbm_dense_wall_mask
+//   LbmContainers::computeRhoAndU   LbmTools.h:384-437      -> nlbm_d3q19_*_dense_rho_u
+//   LbmIterationD3Q19               src/LbmIteration.h:19-101 (two pre-built Skeletons, run() flips the parity)
+//
+// In the reference these are application headers whose device lambdas run through Neon's generic launcher; here every
+// container is a device-managed container whose body is one call into libneon_lbm.so per device.  Nothing here computes.
+#pragma once
+
+#include <ostream>
+#include <type_traits>
+#include <vector>
+
+#include "Neon/Neon.h"
+#include "Neon/domain/dGrid.h"
+#include "Neon/set/Container.h"
+#include "Neon/skeleton/Skeleton.h"
+
+struct CellType
+{
+    enum Classification : int
+    {
+        bounceBack = NLBM_BOUNCE_BACK,
+        movingWall = NLBM_MOVING_WALL,
+        bulk = NLBM_BULK,
+        undefined = NLBM_UNDEFINED
+    };
+    /* the reference's default constructor ignores its argument and yields a bulk cell (CellType.h:13-18) */
+    CellType(int = 0) : wallNghBitflag(0), classification(bulk) {}
+    explicit CellType(Classification c, uint32_t n = 0) : wallNghBitflag(n), classification(c) {}
+    uint32_t       wallNghBitflag;
+    Classification classification;
+};
+inline std::ostream& operator<<(std::ostream& os, const CellType& c)
+{
+    return os << static_cast<double>(c.classification);
+}
+
+namespace Neon::domain {
+/* device representation of CellType: the 32-bit flag word of include/neon_lbm.h */
+template <>
+struct FlagWordCodec<CellType, void>
+{
+    static constexpr bool enabled = true;
+    static uint32_t       pack(const CellType& c)
+    {
+        return (c.wallNghBitflag & NLBM_FLAG_MASK_BITS) | (uint32_t(c.classification) << NLBM_FLAG_CLASS_SHIFT);
+    }
+    static CellType unpack(uint32_t w)
+    {
+        return CellType(static_cast<CellType::Classification>(NLBM_FLAG_CLASS(w)), w & NLBM_FLAG_MASK_BITS);
+    }
+};
+}  // namespace Neon::domain
+
+template <typename StorageFP, typename ComputeFP>
+struct D3Q19Template
+{
+    static constexpr int Q = 19;
+    static constexpr int D = 3;
+    static constexpr int centerDirection = 9;
+    static constexpr int goRangeBegin = 0, goRangeEnd = 8, goBackOffset = 10;
+
+    explicit D3Q19Template(const Neon::Backend&)
+    {
+        /* direction k and k + 10 are opposite; 9 is the rest population */
+        const int go[9][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {0, -1, -1}, {0, -1, 1}};
+        c_vect.resize(Q);
+        t_vect.resize(Q);
+        opp_vect.resize(Q);
+        for (int k = 0; k < 9; ++k) {
+            c_vect[k] = Neon::index_3d(go[k][0], go[k][1], go[k][2]);
+            c_vect[k + goBackOffset] = -c_vect[k];
+            const double w = k < 3 ? 1. / 18. : 1. / 36.;
+            t_vect[k] = t_vect[k + goBackOffset] = w;
+            opp_vect[k] = k + goBackOffset;
+            opp_vect[k + goBackOffset] = k;
+        }
+        c_vect[centerDirection] = Neon::index_3d(0, 0, 0);
+        t_vect[centerDirection] = 1. / 3.;
+        opp_vect[centerDirection] = centerDirection;
+    }
+    template <int go>
+    static constexpr int getOpposite()
+    {
+        return go == centerDirection ? centerDirection : go <= goRangeEnd ? go + goBackOffset : go - goBackOffset;
+    }
+    std::vector<double>         t_vect;
+    std::vector<Neon::index_3d> c_vect;
+    std::vector<int>            opp_vect;
+};
+
+template <typename StorageFP, typename ComputeFP>
+struct D3Q27Template
+{
+    static constexpr int Q = 27;
+    static constexpr int D = 3;
+    static constexpr int centerDirection = 0;
+
+    explicit D3Q27Template(const Neon::Backend&)
+    {
+        /* x slowest (0, -1, +1), then y, then z, each in the order 0, -1, +1 */
+        const int order[3] = {0, -1, 1};
+        for (int ix : order) {
+            for (int iy : order) {
+                for (int iz : order) {
+                    c_vect.emplace_back(ix, iy, iz);
+                    const int nz = (ix != 0) + (iy != 0) + (iz != 0);
+                    t_vect.push_back(nz == 0 ? 8. / 27. : nz == 1 ? 2. / 27. : nz == 2 ? 1. / 54. : 1. / 216.);
+                }
+            }
+        }
+        opp_vect.resize(Q);
+        for (int k = 0; k < Q; ++k) {
+            for (int j = 0; j < Q; ++j) {
+                if (c_vect[j] == -c_vect[k]) {
+                    opp_vect[k] = j;
+                }
+            }
+        }
+    }
+    std::vector<double>         t_vect;
+    std::vector<Neon::index_3d> c_vect;
+    std::vector<int>            opp_vect;
+};
+
+namespace Neon::lbm {
+
+/* process-wide options of the kernel library for containers built afterwards: arithmetic mode (NLBM_ARITH_FAST:
+ * FMAs in the storage precision, within the north-star tolerance; NLBM_ARITH_REFERENCE: the reference's rounding bit
+ * for bit) and tuning bits (NLBM_OPT_*).  They never change which cells are written. */
+inline int& kernelOptions()
+{
+    static int opts = NLBM_ARITH_FAST;
+    return opts;
+}
+
+}  // namespace Neon::lbm
+
+template <typename Lattice, typename PopulationField, typename LbmComputeType>
+struct LbmContainers
+{
+    using LbmStoreType = typename PopulationField::Type;
+    using CellTypeField = typename PopulationField::Grid::template Field<CellType, 1>;
+    using Rho = typename PopulationField::Grid::template Field<LbmStoreType, 1>;
+    using U = typename PopulationField::Grid::template Field<LbmStoreType, 3>;
+
+    /* One fused pull-stream + BGK collide over the cells of the data view.  fIn: const STENCIL read with the given
+     * halo semantic, fOut: MAP write, flags: MAP read (LbmTools.h:296-299). */
+    static auto iteration(Neon::set::StencilSemantic stencilSemantic, const PopulationField& fInField, const CellTypeField& cellTypeField,
+                          const LbmComputeType omega, PopulationField& fOutField) -> Neon::set::Container
+    {
+        using StepFn = int (*)(const nlbm_dense_desc*, double, int, int, void*);
+        StepFn step = nullptr;
+        if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>) {
+            step = nlbm_d3q19_f32_dense_step;
+        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, double>) {
+            step = nlbm_d3q19_f32c64_dense_step;
+        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>) {
+            step = nlbm_d3q19_f64_dense_step;
+        } else if constexpr (Lattice::Q == 27 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>) {
+            step = nlbm_d3q27_f32_dense_step;
+        } else if constexpr (Lattice::Q == 27 && std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>) {
+            step = nlbm_d3q27_f64_dense_step;
+        } else {
+            NEON_THROW_UNSUPPORTED_OPERATION("store/compute precision pair (supported: f/f, f/d (D3Q19), d/d)");
+        }
+        if (fInField.getUid() == fOutField.getUid()) {
+            NEON_THROW_UNSUPPORTED_OPERATION("the pull scheme needs two population fields (LbmIteration.h:38-39)");
+        }
+        if (fInField.getCardinality() != Lattice::Q || fOutField.getCardinality() != Lattice::Q) {
+            NEON_THROW_UNSUPPORTED_OPERATION("population fields must have the lattice's cardinality");
+        }
+        const Neon::Backend bk = fInField.getBackend();
+        const int           opts = Neon::lbm::kernelOptions();
+        const double        om = static_cast<double>(omega);
+        return Neon::set::Container::factoryDeviceManaged(
+            "LBM_iteration_D3Q" + std::to_string(Lattice::Q), bk, [&](Neon::SetIdx setIdx, Neon::set::Loader& L) {
+                auto            fIn = L.load(fInField, Neon::Pattern::STENCIL, stencilSemantic);
+                auto            fOut = L.load(fOutField);
+                auto            flg = L.load(cellTypeField);
+                nlbm_dense_desc d = fIn.desc;
+                d.pop_in = fIn.mem();
+                d.pop_out = fOut.mem();
+                d.flags = flg.mem();
+                const int dev = setIdx.idx;
+                return [=](int streamIdx, Neon::DataView dataView) {
+                    Neon::detail::check(step(&d, om, static_cast<int>(dataView), opts, bk.stream(dev, streamIdx)), "nlbm dense step");
+                };
+            });
+    }
+
+    /* LbmTools.h:344-376, run in place as RunCavityTwoPop.cu:239 does.  The launcher checks the library's count of
+     * bulk-cell neighbours that fall outside the domain (the reference would read invalid data there). */
+    static auto computeWallNghMask(const CellTypeField& infoInField, CellTypeField& infoOutpeField) -> Neon::set::Container
+    {
+        if (infoInField.getUid() != infoOutpeField.getUid()) {
+            NEON_THROW_UNSUPPORTED_OPERATION("the wall mask is built in place (RunCavityTwoPop.cu:239)");
+        }
+        const Neon::Backend bk = infoInField.getBackend();
+        return Neon::set::Container::factoryDeviceManaged(
+            "LBM_computeWallNghMask", bk, [&](Neon::SetIdx setIdx, Neon::set::Loader& L) {
+                auto            in = L.load(infoInField, Neon::Pattern::STENCIL);
+                auto            out = L.load(infoOutpeField);
+                nlbm_dense_desc d = out.desc;
+                d.flags = out.mem();
+                (void)in;
+                const int dev = setIdx.idx;
+                return [=](int streamIdx, Neon::DataView) {
+                    int32_t* bad = nullptr;
+                    NEON_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&bad), sizeof(int32_t)));
+                    cudaStream_t st = bk.stream(dev, streamIdx);
+                    NEON_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
+                    Neon::detail::check(nlbm_dense_wall_mask(&d, Lattice::Q, bad, st), "nlbm_dense_wall_mask");
+                    int32_t nBad = 0;
+                    NEON_CUDA_CHECK(cudaMemcpyAsync(&nBad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                    NEON_CUDA_CHECK(cudaStreamSynchronize(st));
+                    cudaFree(bad);
+                    if (nBad != 0) {
+                        Neon::NeonException e("computeWallNghMask");
+                        e << nBad << " bulk-cell neighbours fall outside the domain: enclose the geometry with non-bulk cells";
+                        NEON_THROW(e);
+                    }
+                };
+            });
+    }
+
+    /* LbmTools.h:384-437 (D3Q19): rho and u of every cell from the populations */
+    static auto computeRhoAndU(const PopulationField& fInField, const CellTypeField& cellTypeField, Rho& rhoField, U& uField)
+        -> Neon::set::Container
+    {
+        using Fn = int (*)(const nlbm_dense_desc*, void*, void*, void*);
+        Fn fn = nullptr;
+        if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float>) {
+            fn = nlbm_d3q19_f32_dense_rho_u;
+        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, double>) {
+            fn = nlbm_d3q19_f64_dense_rho_u;
+        } else {
+            NEON_THROW_UNSUPPORTED_OPERATION("computeRhoAndU is a D3Q19 container (LbmTools.h:384-437)");
+        }
+        const Neon::Backend bk = fInField.getBackend();
+        return Neon::set::Container::factoryDeviceManaged(
+            "LBM_computeRhoAndU", bk, [&](Neon::SetIdx setIdx, Neon::set::Loader& L) {
+                auto            fIn = L.load(fInField, Neon::Pattern::STENCIL);
+                auto            flg = L.load(cellTypeField);
+                auto            rho = L.load(rhoField);
+                auto            u = L.load(uField);
+                nlbm_dense_desc d = fIn.desc;
+                d.pop_in = fIn.mem();
+                d.flags = flg.mem();
+                const int dev = setIdx.idx;
+                return [=](int streamIdx, Neon::DataView) {
+                    Neon::detail::check(fn(&d, rho.mem(), u.mem(), bk.stream(dev, streamIdx)), "nlbm dense rho_u");
+                };
+            });
+    }
+};
+
+/* LbmIteration.h:19-101, for both lattices: skeleton 0 streams pop0 -> pop1, skeleton 1 pop1 -> pop0 */
+template <typename Lattice, typename PopulationField, typename LbmComputeType>
+struct LbmIterationT
+{
+    using LbmStoreType = typename PopulationField::Type;
+    using CellTypeField = typename PopulationField::Grid::template Field<CellType, 1>;
+    using LbmTools = LbmContainers<Lattice, PopulationField, LbmComputeType>;
+
+    LbmIterationT(Neon::set::StencilSemantic stencilSemantic, Neon::skeleton::Occ occ, Neon::set::TransferMode transfer,
+                  PopulationField& fIn, PopulationField& fOut, CellTypeField& cellTypeField, LbmComputeType omega, bool cudaGraph = false)
+    {
+        pop[0] = fIn;
+        pop[1] = fOut;
+        for (int target = 0; target < 2; ++target) {
+            std::vector<Neon::set::Container> ops;
+            ops.push_back(LbmTools::iteration(stencilSemantic, pop[target], cellTypeField, omega, pop[1 - target]));
+            lbmTwoPop[target] = Neon::skeleton::Skeleton(fIn.getBackend());
+            lbmTwoPop[target].sequence(ops, "LBM_iteration_" + std::to_string(target), Neon::skeleton::Options(occ, transfer, cudaGraph));
+        }
+    }
+    auto getInput() -> PopulationField& { return pop[parity]; }
+    auto getOutput() -> PopulationField& { return pop[1 - parity]; }
+    auto run() -> void
+    {
+        lbmTwoPop[parity].run();
+        parity = 1 - parity;
+    }
+    auto sync() -> void { pop[0].getBackend().syncAll(); }
+    auto skeleton(int target) -> Neon::skeleton::Skeleton& { return lbmTwoPop[target]; }
+
+   private:
+    Neon::skeleton::Skeleton lbmTwoPop[2];
+    PopulationField          pop[2];
+    int                      parity = 0;
+};
+
+template <typename PopulationField, typename LbmComputeType>
+using LbmIterationD3Q19 = LbmIterationT<D3Q19Template<typename PopulationField::Type, LbmComputeType>, PopulationField, LbmComputeType>;
+template <typename PopulationField, typename LbmComputeType>
+using LbmIterationD3Q27 = LbmIterationT<D3Q27Template<typename PopulationField::Type, LbmComputeType>, PopulationField, LbmComputeType>;

@@ -1,0 +1,162 @@
+"""The C++ host veneer (neon_b200/cpp: Neon:: names over the C ABI) and the lid-driven-cavity benchmark built on it.
+
+CPU part: it builds, fails loudly without a device, rejects bad command lines.
+GPU part (-m gpu): the benchmark binary — the reference's own flow: host forEachActiveCell set-up, updateDeviceData, flag
+halo update, computeWallNghMask, LbmIterationD3Q19 over Skeletons — reproduces the golden dumps of the UNMODIFIED
+reference bit for bit in REFERENCE arithmetic, on one partition and on 2-4 partitions with every OCC / transfer mode /
+halo semantic; D3Q27 against the oracle; the --visual profiles against the known answers of the stock reference run
+(SURVEY.md §8c).
+"""
+import glob
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPP = os.path.join(ROOT, "neon_b200", "cpp")
+APP = os.path.join(CPP, "bin", "lbm-lid-driven-cavity-flow")
+
+
+@pytest.fixture(scope="module")
+def app():
+    if not os.path.exists(os.path.join(ROOT, "neon_b200", "lib", "libneon_lbm.so")):
+        from neon_b200 import build as B
+        B.build()
+    subprocess.check_call(["make", "-s", "-C", CPP])
+    assert os.path.exists(APP)
+    return APP
+
+
+def run_app(app, args, cwd, check=True):
+    r = subprocess.run([app] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    if check:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r
+
+
+# ------------------------------------------------------------------------------------------------------------ CPU
+def test_builds_and_links_the_kernel_library(app):
+    out = subprocess.run(["ldd", app], capture_output=True, text=True).stdout
+    assert "libneon_lbm.so" in out and "not found" not in out.split("libneon_lbm.so")[1].split("\n")[0]
+
+
+def test_bad_command_line_prints_synopsis(app, tmp_path):
+    r = run_app(app, ["--deviceType", "gpu"], tmp_path, check=False)
+    assert r.returncode != 0 and "SYNOPSIS" in r.stdout
+    r = run_app(app, ["--deviceType", "gpu", "--deviceIds", "0", "--frobnicate"], tmp_path, check=False)
+    assert r.returncode != 0 and "unknown option --frobnicate" in r.stdout
+
+
+def test_cpu_device_type_is_refused(app, tmp_path):
+    """north star: no CPU fallback — the reference's CPU numbers come from the reference itself"""
+    r = run_app(app, ["--deviceType", "cpu", "--deviceIds", "0", "--domain-size", "16", "--max-iter", "2", "--benchmark"], tmp_path,
+                check=False)
+    assert r.returncode == 1 and "no CPU compute path" in r.stderr
+
+
+def test_fails_loudly_without_a_device(app, tmp_path):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = run_app(app, ["--deviceType", "gpu", "--deviceIds", "0", "--domain-size", "16", "--max-iter", "2", "--benchmark"], tmp_path,
+                check=False)
+    assert r.returncode == 1 and "NeonException" in r.stderr and "no CPU fallback" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU
+GOLDEN = [  # name, dim, fp, geom
+    ("cavity16_f32", (16, 16, 16), "float", "cavity"),
+    ("sphere16_f64", (16, 16, 16), "double", "sphere"),
+    ("sphere24_f32", (24, 24, 24), "float", "sphere"),
+    ("sphere20x12x16_f32", (20, 12, 16), "float", "sphere"),
+    ("cavity12_f64", (12, 12, 12), "double", "cavity"),
+]
+
+
+def _dump(app, tmp_path, dim, fp, geom, iters, extra=(), devices=(0,), arith="reference", lattice="D3Q19"):
+    out = os.path.join(tmp_path, "dump.bin")
+    args = ["--deviceType", "gpu", "--deviceIds", *devices, "--grid", "dGrid", "--dim", *dim, "--max-iter", iters, "--warmup-iter", 0,
+            "--computeFP", fp, "--storageFP", fp, "--benchmark", "--geom", geom, "--arith", arith, "--lattice", lattice, "--dump", out,
+            "--report-filename", os.path.join(tmp_path, "report"), *extra]
+    run_app(app, args, tmp_path)
+    from oracle import oracle as O
+    return O.read_ref_dump(out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dim,fp,geom", GOLDEN)
+def test_benchmark_flow_reproduces_the_reference_dumps(app, tmp_path, golden_dir, name, dim, fp, geom):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    d = _dump(app, str(tmp_path), dim, fp, geom, int(g["iters"]))
+    assert abs(d["omega"] - float(g["omega"])) == 0.0
+    assert np.array_equal(d["cls"], g["cls"]) and np.array_equal(d["mask"], g["mask"]), "flags / wall masks must be bit-exact"
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8)), "REFERENCE arithmetic must be bit-exact"
+    # the default (FAST) arithmetic stays within the north-star tolerance
+    f = _dump(app, str(tmp_path), dim, fp, geom, int(g["iters"]), arith="fast")
+    tol = 1e-5 if fp == "float" else 1e-12
+    assert np.abs(f["pop"].astype(np.float64) - g["pop"]).max() / np.abs(g["pop"]).max() < tol
+    rep = glob.glob(os.path.join(str(tmp_path), "report_*.json"))
+    assert rep, "no report written"
+    j = json.load(open(rep[0]))
+    for key in ("Re", "ulb", "N", "omega", "occ", "transferMode", "transferSemantic", "MLUPS", "Loop Time (microseconds)",
+                "Problem Setup Time (microseconds)", "Neon Grid Init Time (microseconds)", "Backend"):
+        assert key in j, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [2, 3, 4])
+@pytest.mark.parametrize("occ", ["--nOCC", "--sOCC"])
+@pytest.mark.parametrize("mode", ["--get", "--put"])
+@pytest.mark.parametrize("sem", ["--huLattice", "--huGrid"])
+def test_partitions_match_the_single_partition_reference(app, tmp_path, golden_dir, parts, occ, mode, sem):
+    """several z-slab partitions (an oversubscribed device list, as the reference's domain tests use) == 1 partition"""
+    g = np.load(os.path.join(golden_dir, "sphere24_f32.npz"))
+    d = _dump(app, str(tmp_path), (24, 24, 24), "float", "sphere", int(g["iters"]), extra=(occ, mode, sem), devices=(0,) * parts)
+    assert np.array_equal(d["mask"], g["mask"])
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8))
+
+
+@pytest.mark.gpu
+def test_ragged_partitions_and_device_setup(app, tmp_path, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sphere20x12x16_f32.npz"))
+    for extra in (("--sOCC",), ("--sOCC", "--device-setup"), ("--nOCC", "--device-setup", "--put")):
+        d = _dump(app, str(tmp_path), (20, 12, 16), "float", "sphere", int(g["iters"]), extra=extra, devices=(0, 0, 0))
+        assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8)), extra
+    d = _dump(app, str(tmp_path), (20, 12, 16), "float", "sphere", int(g["iters"]), extra=("--graph",))
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8)), "CUDA-graph replay"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fp,parts", [("double", 1), ("double", 3), ("float", 2)])
+def test_d3q27_against_the_oracle(app, tmp_path, oracle, fp, parts):
+    O = oracle
+    n, iters = 20, 12
+    dt = np.float64 if fp == "double" else np.float32
+    cls = O.classify(O.GEOM_CAVITY_SPHERE, n, n, n)
+    mask = O.wall_mask(27, cls)
+    ref = O.run(27, O.init_pop(27, cls, dt), cls, mask, O.omega_cavity(n), iters)
+    d = _dump(app, str(tmp_path), (n, n, n), fp, "sphere", iters, extra=("--sOCC",), devices=(0,) * parts, lattice="D3Q27")
+    assert np.array_equal(d["mask"], mask)
+    assert np.array_equal(d["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.gpu
+def test_visual_mode_profiles_match_the_stock_reference_run(app, tmp_path):
+    """Known answers of the UNMODIFIED reference's --visual run, N=64 fp32, state after 100 iterations."""
+    run_app(app, ["--deviceType", "gpu", "--deviceIds", "0", "--domain-size", "64", "--max-iter", "101", "--computeFP", "float",
+                  "--storageFP", "float", "--visual", "--arith", "reference", "--report-filename", os.path.join(str(tmp_path), "r")],
+            str(tmp_path))
+    y = np.loadtxt(os.path.join(str(tmp_path), "NeonUniformLBM_00100_Y.dat"))
+    x = np.loadtxt(os.path.join(str(tmp_path), "NeonUniformLBM_00100_X.dat"))
+    known_y = {0.125: -2.29027e-05, 0.25: -0.000560718, 0.5: -0.00134673, 0.75: -0.00235457, 0.875: -0.00266163,
+               0.96875: 0.0323317, 0.984375: 0.04}
+    known_x = {0.125: 0.0013653, 0.5: -2.50035e-05, 0.875: -0.00140206}
+    for tab, known in ((y, known_y), (x, known_x)):
+        for pos, val in known.items():
+            row = tab[np.argmin(np.abs(tab[:, 0] - pos))]
+            assert abs(row[0] - pos) < 1e-9
+            assert abs(row[1] - val) <= 1e-6 * max(1e-3, abs(val)) + 5e-6 * abs(val), (pos, row[1], val)
+    assert os.path.exists(os.path.join(str(tmp_path), "u_00100.vtk")) and os.path.exists(os.path.join(str(tmp_path), "rho_00000.vtk"))

@@ -24,6 +24,7 @@
 
 #include "Neon/Neon.h"
 #include "Neon/Report.h"
+#include "Neon/domain/bGrid.h"
 #include "Neon/domain/dGrid.h"
 #include "Neon/lbm/Lbm.h"
 #include "Neon/set/Backend.h"
@@ -71,7 +72,7 @@ struct Config
     static void usage(const char* argv0)
     {
         std::cout << "SYNOPSIS\n  " << argv0
-                  << " --deviceType <cpu|gpu> --deviceIds <id>... [--grid <dGrid>] [--domain-size <N>] [--warmup-iter <W>]\n"
+                  << " --deviceType <cpu|gpu> --deviceIds <id>... [--grid <dGrid|bGrid>] [--domain-size <N>] [--warmup-iter <W>]\n"
                      "      [--max-iter <M>] [--repetitions <R>] [--report-filename <F>] [--computeFP <float|double>]\n"
                      "      [--storageFP <float|double>] [--sOCC|--nOCC] [--put|--get] [--huLattice|--huGrid] [--benchmark|--visual] [--vti]\n"
                      "      [--lattice <D3Q19|D3Q27>] [--arith <fast|reference>] [--geom <cavity|sphere>] [--dim <NX> <NY> <NZ>]\n"
@@ -333,16 +334,28 @@ void run(Config& config, RunReport& report)
     };
     if (config.deviceSetup) {
         /* classes, wall masks and initial populations produced on the device */
+        const int geomId = config.geom == "sphere" ? 1 : 0;
         for (int d = 0; d < bk.getDeviceCount(); ++d) {
             bk.setDevice(d);
-            nlbm_dense_desc desc = pop0.getPartition(d).desc;
+            auto desc = pop0.getPartition(d).desc; /* nlbm_dense_desc or nlbm_block_desc */
             desc.flags = flag.getPartition(d).mem();
             cudaStream_t st = bk.stream(d, 0);
-            Neon::detail::check(nlbm_dense_classify(&desc, config.geom == "sphere" ? 1 : 0, nullptr, st), "nlbm_dense_classify");
-            Neon::detail::check(nlbm_dense_wall_mask(&desc, Lattice::Q, nullptr, st), "nlbm_dense_wall_mask");
+            if constexpr (std::is_same_v<Grid, Neon::bGrid>) {
+                Neon::detail::check(nlbm_block_classify(&desc, geomId, nullptr, grid.activeMaskDev(d), st), "nlbm_block_classify");
+                Neon::detail::check(nlbm_block_wall_mask(&desc, Lattice::Q, nullptr, st), "nlbm_block_wall_mask");
+            } else {
+                Neon::detail::check(nlbm_dense_classify(&desc, geomId, nullptr, st), "nlbm_dense_classify");
+                Neon::detail::check(nlbm_dense_wall_mask(&desc, Lattice::Q, nullptr, st), "nlbm_dense_wall_mask");
+            }
             for (auto* f : {&pop0, &pop1}) {
                 desc.pop_out = f->getPartition(d).mem();
-                if constexpr (std::is_same_v<StorageFP, float>) {
+                if constexpr (std::is_same_v<Grid, Neon::bGrid>) {
+                    if constexpr (std::is_same_v<StorageFP, float>) {
+                        Neon::detail::check(nlbm_block_init_pop_f32(&desc, Lattice::Q, ulb, st), "nlbm_block_init_pop_f32");
+                    } else {
+                        Neon::detail::check(nlbm_block_init_pop_f64(&desc, Lattice::Q, ulb, st), "nlbm_block_init_pop_f64");
+                    }
+                } else if constexpr (std::is_same_v<StorageFP, float>) {
                     Neon::detail::check(nlbm_dense_init_pop_f32(&desc, Lattice::Q, ulb, st), "nlbm_dense_init_pop_f32");
                 } else {
                     Neon::detail::check(nlbm_dense_init_pop_f64(&desc, Lattice::Q, ulb, st), "nlbm_dense_init_pop_f64");
@@ -377,7 +390,7 @@ void run(Config& config, RunReport& report)
 
     // ---- --visual: rho/u export every 100 iterations (RunCavityTwoPop.cu:82-150) --------------------------------------
     auto exportRhoAndU = [&](int iterationId) {
-        if constexpr (Lattice::Q == 19) {
+        if constexpr (Lattice::Q == 19 && std::is_same_v<Grid, Neon::dGrid>) {
             if (iterationId % 100 != 0) {
                 return;
             }
@@ -510,8 +523,10 @@ int main(int argc, char* argv[])
         for (int r = 0; r < config.repetitions; ++r) {
             if (config.gridType == "dGrid") {
                 runPrecision<Neon::dGrid>(config, report);
+            } else if (config.gridType == "bGrid") {
+                runPrecision<Neon::bGrid>(config, report);
             } else {
-                NEON_THROW_UNSUPPORTED_OPERATION("grid " + config.gridType + " in the C++ veneer (dGrid here; bGrid through neon_b200.bGrid)");
+                NEON_THROW_UNSUPPORTED_OPERATION("grid " + config.gridType + " (dGrid and bGrid are on the accelerated path; eGrid is not)");
             }
         }
         report.save();

@@ -391,14 +391,31 @@ class bField
         return p;
     }
 
-    T& getReference(const index_3d& p, int card) { return mS->host[hostOffset(p, card)]; }
-    T  operator()(const index_3d& p, int card) const { return mS->grid.isActive(p) ? mS->host[hostOffset(p, card)] : mS->outside; }
-    T*       hostData() { return mS->host.data(); }
-    const T* hostData() const { return mS->host.data(); }
+    T& getReference(const index_3d& p, int card)
+    {
+        ensureHost();
+        return mS->host[hostOffset(p, card)];
+    }
+    T operator()(const index_3d& p, int card) const
+    {
+        ensureHost();
+        return mS->grid.isActive(p) ? mS->host[hostOffset(p, card)] : mS->outside;
+    }
+    T* hostData()
+    {
+        ensureHost();
+        return mS->host.data();
+    }
+    const T* hostData() const
+    {
+        ensureHost();
+        return mS->host.data();
+    }
 
     template <typename Fn>
     void forEachActiveCell(Fn fn, computeMode_t mode = computeMode_t::par)
     {
+        ensureHost();
         const bGrid&   g = mS->grid;
         const index_3d dim = g.getDimension();
         const int      card = mS->cardinality;
@@ -514,7 +531,7 @@ class bField
         s.cardinality = cardinality;
         s.outside = outside;
         s.uid = uid;
-        s.host.assign(grid.getDimension().template rMul<size_t>() * size_t(cardinality), outside);
+        /* host mirror and staging buffers are allocated at their first use (ensureHost) */
         const Backend& bk = grid.getBackend();
         for (int d = 0; d < grid.getNumPartitions(); ++d) {
             const size_t n = size_t(cardinality) * std::max<uint32_t>(grid.partition(d).nAlloc, 1) * detail::kBlockCells;
@@ -524,7 +541,6 @@ class bField
                 bk.setDevice(d);
                 NEON_CUDA_CHECK(cudaMalloc(&p, n * sizeof(DeviceType)));
                 NEON_CUDA_CHECK(cudaMemset(p, 0, n * sizeof(DeviceType)));
-                NEON_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&st), n * sizeof(DeviceType), cudaHostAllocDefault));
             }
             s.dev.push_back(p);
             s.staging.push_back(st);
@@ -535,6 +551,20 @@ class bField
     {
         const index_3d& dim = mS->grid.getDimension();
         return (size_t(card) * dim.z + p.z) * size_t(dim.y) * dim.x + size_t(p.y) * dim.x + p.x;
+    }
+
+    void ensureHost() const
+    {
+        auto& s = *mS;
+        if (!s.host.empty()) {
+            return;
+        }
+        s.host.assign(s.grid.getDimension().template rMul<size_t>() * size_t(s.cardinality), s.outside);
+        const Backend& bk = s.grid.getBackend();
+        for (int d = 0; bk.runtime() == Runtime::stream && d < s.grid.getNumPartitions(); ++d) {
+            const size_t n = size_t(s.cardinality) * std::max<uint32_t>(s.grid.partition(d).nAlloc, 1) * detail::kBlockCells;
+            NEON_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&s.staging[d]), n * sizeof(DeviceType), cudaHostAllocDefault));
+        }
     }
 
     static DeviceType toDevice(const T& v)
@@ -559,6 +589,7 @@ class bField
         using namespace detail;
         const bGrid&   g = mS->grid;
         const Backend& bk = g.getBackend();
+        ensureHost();
         if (bk.runtime() != Runtime::stream) {
             return;
         }

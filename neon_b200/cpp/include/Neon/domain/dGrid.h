@@ -348,18 +348,32 @@ class dField
     bool isValid() const { return bool(mS); }
 
     // ---- host mirror ---------------------------------------------------------------------------------------------
-    T& getReference(const index_3d& p, int card) { return mS->host[hostOffset(p, card)]; }
-    T  operator()(const index_3d& p, int card) const
+    T& getReference(const index_3d& p, int card)
     {
+        ensureHost();
+        return mS->host[hostOffset(p, card)];
+    }
+    T operator()(const index_3d& p, int card) const
+    {
+        ensureHost();
         return mS->grid.isInsideDomain(p) ? mS->host[hostOffset(p, card)] : mS->outside;
     }
-    T*       hostData() { return mS->host; } /* [cardinality][z][y][x], unpadded */
-    const T* hostData() const { return mS->host; }
+    T* hostData() /* [cardinality][z][y][x], unpadded */
+    {
+        ensureHost();
+        return mS->host;
+    }
+    const T* hostData() const
+    {
+        ensureHost();
+        return mS->host;
+    }
 
     /* fn(const index_3d&, const int& cardinality, T&) over every cell of the host mirror */
     template <typename Fn>
     void forEachActiveCell(Fn fn, computeMode_t mode = computeMode_t::par)
     {
+        ensureHost();
         const index_3d dim = getDimension();
         const int      card = mS->cardinality;
         T*             host = mS->host;
@@ -461,6 +475,7 @@ class dField
         if constexpr (kFlagWords) {
             NEON_THROW_UNSUPPORTED_OPERATION("VTK export of a flag field");
         } else {
+            ensureHost();
             const index_3d dim = getDimension();
             std::ofstream  out(fileName + ".vtk", std::ios::out | std::ios::binary);
             if (!out) {
@@ -544,16 +559,9 @@ class dField
         s.outside = outside;
         s.uid = uid;
         const Backend& bk = grid.getBackend();
-        const size_t   n = grid.getNumActiveCells() * size_t(cardinality);
         const bool     cuda = bk.runtime() == Runtime::stream;
-        /* the host mirror is pinned when it will be copied to a device (asynchronous, full-rate transfers) */
-        if (cuda && cudaHostAlloc(reinterpret_cast<void**>(&s.host), n * sizeof(T), cudaHostAllocDefault) == cudaSuccess) {
-            s.hostPinned = true;
-        } else {
-            (void)cudaGetLastError();
-            s.host = new T[n];
-        }
-        std::fill(s.host, s.host + n, outside);
+        /* the host mirror is allocated at its first use (ensureHost): a run that sets the problem up on the device and
+         * never reads fields back needs none */
         for (int d = 0; d < grid.getNumPartitions(); ++d) {
             nlbm_dense_desc desc = grid.descOf(d);
             size_t          bytes = 0;
@@ -583,6 +591,31 @@ class dField
         }
     }
 
+    /* pinned when it will be copied to a device (asynchronous, full-rate transfers); filled with the outside value */
+    void ensureHost() const
+    {
+        auto& s = *mS;
+        if (s.host) {
+            return;
+        }
+        const size_t n = s.grid.getNumActiveCells() * size_t(s.cardinality);
+        const bool   cuda = s.grid.getBackend().runtime() == Runtime::stream;
+        if (cuda && cudaHostAlloc(reinterpret_cast<void**>(&s.host), n * sizeof(T), cudaHostAllocDefault) == cudaSuccess) {
+            s.hostPinned = true;
+        } else {
+            (void)cudaGetLastError();
+            s.host = new T[n];
+        }
+        const T outside = s.outside;
+        T*      host = s.host;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+        for (int64_t i = 0; i < int64_t(n); ++i) {
+            host[i] = outside;
+        }
+    }
+
     size_t hostOffset(const index_3d& p, int card) const
     {
         const index_3d& dim = mS->grid.getDimension();
@@ -593,6 +626,7 @@ class dField
     {
         const dGrid&   g = mS->grid;
         const Backend& bk = g.getBackend();
+        ensureHost();
         if (bk.runtime() != Runtime::stream) {
             return; /* host-only backend: the mirror is the field */
         }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "Neon/Neon.h"
+#include "Neon/domain/bGrid.h"
 #include "Neon/domain/dGrid.h"
 #include "Neon/set/Container.h"
 #include "Neon/skeleton/Skeleton.h"
@@ -155,20 +156,38 @@ struct LbmContainers
     static auto iteration(Neon::set::StencilSemantic stencilSemantic, const PopulationField& fInField, const CellTypeField& cellTypeField,
                           const LbmComputeType omega, PopulationField& fOutField) -> Neon::set::Container
     {
-        using StepFn = int (*)(const nlbm_dense_desc*, double, int, int, void*);
-        StepFn step = nullptr;
-        if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>) {
-            step = nlbm_d3q19_f32_dense_step;
-        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, double>) {
-            step = nlbm_d3q19_f32c64_dense_step;
-        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>) {
-            step = nlbm_d3q19_f64_dense_step;
-        } else if constexpr (Lattice::Q == 27 && std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>) {
-            step = nlbm_d3q27_f32_dense_step;
-        } else if constexpr (Lattice::Q == 27 && std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>) {
-            step = nlbm_d3q27_f64_dense_step;
+        constexpr bool isBlock = std::is_same_v<typename PopulationField::Grid, Neon::bGrid>;
+        using Desc = std::conditional_t<isBlock, nlbm_block_desc, nlbm_dense_desc>;
+        using StepFn = int (*)(const Desc*, double, int, int, void*);
+        constexpr bool f32 = std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>;
+        constexpr bool f64 = std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>;
+        constexpr bool f32c64 = std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, double>;
+        StepFn         step = nullptr;
+        if constexpr (isBlock) {
+            if constexpr (Lattice::Q == 19 && f32) {
+                step = nlbm_d3q19_f32_block_step;
+            } else if constexpr (Lattice::Q == 19 && f64) {
+                step = nlbm_d3q19_f64_block_step;
+            } else if constexpr (Lattice::Q == 27 && f32) {
+                step = nlbm_d3q27_f32_block_step;
+            } else if constexpr (Lattice::Q == 27 && f64) {
+                step = nlbm_d3q27_f64_block_step;
+            }
         } else {
-            NEON_THROW_UNSUPPORTED_OPERATION("store/compute precision pair (supported: f/f, f/d (D3Q19), d/d)");
+            if constexpr (Lattice::Q == 19 && f32) {
+                step = nlbm_d3q19_f32_dense_step;
+            } else if constexpr (Lattice::Q == 19 && f32c64) {
+                step = nlbm_d3q19_f32c64_dense_step;
+            } else if constexpr (Lattice::Q == 19 && f64) {
+                step = nlbm_d3q19_f64_dense_step;
+            } else if constexpr (Lattice::Q == 27 && f32) {
+                step = nlbm_d3q27_f32_dense_step;
+            } else if constexpr (Lattice::Q == 27 && f64) {
+                step = nlbm_d3q27_f64_dense_step;
+            }
+        }
+        if (step == nullptr) {
+            NEON_THROW_UNSUPPORTED_OPERATION("store/compute precision pair (dGrid: f/f, f/d (D3Q19), d/d; bGrid: f/f, d/d)");
         }
         if (fInField.getUid() == fOutField.getUid()) {
             NEON_THROW_UNSUPPORTED_OPERATION("the pull scheme needs two population fields (LbmIteration.h:38-39)");
@@ -184,13 +203,13 @@ struct LbmContainers
                 auto            fIn = L.load(fInField, Neon::Pattern::STENCIL, stencilSemantic);
                 auto            fOut = L.load(fOutField);
                 auto            flg = L.load(cellTypeField);
-                nlbm_dense_desc d = fIn.desc;
+                Desc            d = fIn.desc;
                 d.pop_in = fIn.mem();
                 d.pop_out = fOut.mem();
                 d.flags = flg.mem();
                 const int dev = setIdx.idx;
                 return [=](int streamIdx, Neon::DataView dataView) {
-                    Neon::detail::check(step(&d, om, static_cast<int>(dataView), opts, bk.stream(dev, streamIdx)), "nlbm dense step");
+                    Neon::detail::check(step(&d, om, static_cast<int>(dataView), opts, bk.stream(dev, streamIdx)), "nlbm step");
                 };
             });
     }
@@ -206,8 +225,8 @@ struct LbmContainers
         return Neon::set::Container::factoryDeviceManaged(
             "LBM_computeWallNghMask", bk, [&](Neon::SetIdx setIdx, Neon::set::Loader& L) {
                 auto            in = L.load(infoInField, Neon::Pattern::STENCIL);
-                auto            out = L.load(infoOutpeField);
-                nlbm_dense_desc d = out.desc;
+                auto out = L.load(infoOutpeField);
+                auto d = out.desc; /* nlbm_dense_desc or nlbm_block_desc */
                 d.flags = out.mem();
                 (void)in;
                 const int dev = setIdx.idx;
@@ -216,7 +235,11 @@ struct LbmContainers
                     NEON_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&bad), sizeof(int32_t)));
                     cudaStream_t st = bk.stream(dev, streamIdx);
                     NEON_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
-                    Neon::detail::check(nlbm_dense_wall_mask(&d, Lattice::Q, bad, st), "nlbm_dense_wall_mask");
+                    if constexpr (std::is_same_v<decltype(d), nlbm_block_desc>) {
+                        Neon::detail::check(nlbm_block_wall_mask(&d, Lattice::Q, bad, st), "nlbm_block_wall_mask");
+                    } else {
+                        Neon::detail::check(nlbm_dense_wall_mask(&d, Lattice::Q, bad, st), "nlbm_dense_wall_mask");
+                    }
                     int32_t nBad = 0;
                     NEON_CUDA_CHECK(cudaMemcpyAsync(&nBad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
                     NEON_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -236,7 +259,9 @@ struct LbmContainers
     {
         using Fn = int (*)(const nlbm_dense_desc*, void*, void*, void*);
         Fn fn = nullptr;
-        if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float>) {
+        if constexpr (std::is_same_v<typename PopulationField::Grid, Neon::bGrid>) {
+            NEON_THROW_UNSUPPORTED_OPERATION("computeRhoAndU on bGrid (the library exports the dense variant; use dGrid for --visual)");
+        } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, float>) {
             fn = nlbm_d3q19_f32_dense_rho_u;
         } else if constexpr (Lattice::Q == 19 && std::is_same_v<LbmStoreType, double>) {
             fn = nlbm_d3q19_f64_dense_rho_u;
@@ -249,14 +274,18 @@ struct LbmContainers
                 auto            fIn = L.load(fInField, Neon::Pattern::STENCIL);
                 auto            flg = L.load(cellTypeField);
                 auto            rho = L.load(rhoField);
-                auto            u = L.load(uField);
-                nlbm_dense_desc d = fIn.desc;
-                d.pop_in = fIn.mem();
-                d.flags = flg.mem();
+                auto      u = L.load(uField);
                 const int dev = setIdx.idx;
-                return [=](int streamIdx, Neon::DataView) {
-                    Neon::detail::check(fn(&d, rho.mem(), u.mem(), bk.stream(dev, streamIdx)), "nlbm dense rho_u");
-                };
+                if constexpr (std::is_same_v<typename PopulationField::Grid, Neon::bGrid>) {
+                    return std::function<void(int, Neon::DataView)>();
+                } else {
+                    nlbm_dense_desc d = fIn.desc;
+                    d.pop_in = fIn.mem();
+                    d.flags = flg.mem();
+                    return std::function<void(int, Neon::DataView)>([=](int streamIdx, Neon::DataView) {
+                        Neon::detail::check(fn(&d, rho.mem(), u.mem(), bk.stream(dev, streamIdx)), "nlbm dense rho_u");
+                    });
+                }
             });
     }
 };

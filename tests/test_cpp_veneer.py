@@ -160,3 +160,57 @@ def test_visual_mode_profiles_match_the_stock_reference_run(app, tmp_path):
             assert abs(row[0] - pos) < 1e-9
             assert abs(row[1] - val) <= 1e-6 * max(1e-3, abs(val)) + 5e-6 * abs(val), (pos, row[1], val)
     assert os.path.exists(os.path.join(str(tmp_path), "u_00100.vtk")) and os.path.exists(os.path.join(str(tmp_path), "rho_00000.vtk"))
+
+
+# ------------------------------------------------------------------------------------------------------------ bGrid
+def _dump_grid(app, tmp_path, grid, *a, **k):
+    extra = tuple(k.pop("extra", ())) + ("--grid", grid)
+    return _dump(app, tmp_path, *a, extra=extra, **k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dim,fp,geom", GOLDEN)
+def test_bgrid_reproduces_the_reference_dumps(app, tmp_path, golden_dir, name, dim, fp, geom):
+    """bGrid (8^3 blocks) gives the same bytes as dGrid — as it does in the reference — including
+    boxes that are not a multiple of the block edge."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    d = _dump_grid(app, str(tmp_path), "bGrid", dim, fp, geom, int(g["iters"]))
+    assert np.array_equal(d["cls"], g["cls"]) and np.array_equal(d["mask"], g["mask"])
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8))
+    d = _dump_grid(app, str(tmp_path), "bGrid", dim, fp, geom, int(g["iters"]), extra=("--device-setup",))
+    assert np.array_equal(d["mask"], g["mask"])
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts,occ,mode,sem", [(2, "--sOCC", "--get", "--huLattice"), (2, "--nOCC", "--put", "--huGrid"),
+                                                (3, "--sOCC", "--put", "--huLattice"), (3, "--nOCC", "--get", "--huLattice")])
+def test_bgrid_partitions_match_the_oracle(app, tmp_path, oracle, parts, occ, mode, sem):
+    """bGrid over several block-layer partitions with a per-cardinality halo (the reference's is NaN for Q = 19)"""
+    O = oracle
+    dim, iters = (24, 16, 48), 12  # 6 block layers
+    cls = O.classify(O.GEOM_CAVITY_SPHERE, *dim)
+    mask = O.wall_mask(19, cls)
+    ref = O.run(19, O.init_pop(19, cls, np.float32), cls, mask, O.omega_cavity(dim[0]), iters)
+    d = _dump_grid(app, str(tmp_path), "bGrid", dim, "float", "sphere", iters, extra=(occ, mode, sem), devices=(0,) * parts)
+    assert np.array_equal(d["mask"], mask)
+    assert np.array_equal(d["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,extra", [("dGrid", ("--sOCC", "--get")), ("dGrid", ("--nOCC", "--put")), ("dGrid", ("--sOCC", "--put", "--huGrid")),
+                                        ("bGrid", ("--sOCC", "--get")), ("bGrid", ("--nOCC", "--put"))])
+def test_two_real_devices_one_process(app, tmp_path, oracle, grid, extra):
+    """the reference's process model: ONE process drives both GPUs; faces move as peer stores/loads over NVLink, ordered by
+    CUDA events across the devices"""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    O = oracle
+    dim, iters = (40, 24, 32), 25
+    cls = O.classify(O.GEOM_CAVITY_SPHERE, *dim)
+    mask = O.wall_mask(19, cls)
+    ref = O.run(19, O.init_pop(19, cls, np.float32), cls, mask, O.omega_cavity(dim[0]), iters)
+    d = _dump_grid(app, str(tmp_path), grid, dim, "float", "sphere", iters, extra=extra, devices=(0, 1))
+    assert np.array_equal(d["mask"], mask)
+    assert np.array_equal(d["pop"].view(np.uint8), ref.view(np.uint8))

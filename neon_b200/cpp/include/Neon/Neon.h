@@ -20,6 +20,17 @@
 
 #include "neon_lbm.h"
 
+/* libNeonCore/include/Neon/core/types/Macros.h:80-106 — host code compiled by g++ sees empty qualifiers */
+#ifdef __CUDACC__
+#define NEON_CUDA_HOST_DEVICE __host__ __device__
+#define NEON_CUDA_DEVICE_ONLY __device__
+#define NEON_CUDA_HOST_ONLY __host__
+#else
+#define NEON_CUDA_HOST_DEVICE
+#define NEON_CUDA_DEVICE_ONLY
+#define NEON_CUDA_HOST_ONLY
+#endif
+
 namespace Neon {
 
 // ---------------------------------------------------------------------------------------------------- small vectors
@@ -34,20 +45,20 @@ struct Vec_3d
         };
         T v[3];
     };
-    constexpr Vec_3d() : x(0), y(0), z(0) {}
-    constexpr Vec_3d(T a) : x(a), y(a), z(a) {}
-    constexpr Vec_3d(T a, T b, T c) : x(a), y(b), z(c) {}
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d() : x(0), y(0), z(0) {}
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d(T a) : x(a), y(a), z(a) {}
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d(T a, T b, T c) : x(a), y(b), z(c) {}
     template <typename U>
-    constexpr explicit Vec_3d(const Vec_3d<U>& o) : x(T(o.x)), y(T(o.y)), z(T(o.z))
+    NEON_CUDA_HOST_DEVICE constexpr explicit Vec_3d(const Vec_3d<U>& o) : x(T(o.x)), y(T(o.y)), z(T(o.z))
     {
     }
-    constexpr bool operator==(const Vec_3d& o) const { return x == o.x && y == o.y && z == o.z; }
-    constexpr bool operator!=(const Vec_3d& o) const { return !(*this == o); }
-    constexpr Vec_3d operator+(const Vec_3d& o) const { return {T(x + o.x), T(y + o.y), T(z + o.z)}; }
-    constexpr Vec_3d operator-(const Vec_3d& o) const { return {T(x - o.x), T(y - o.y), T(z - o.z)}; }
-    constexpr Vec_3d operator-() const { return {T(-x), T(-y), T(-z)}; }
+    NEON_CUDA_HOST_DEVICE constexpr bool operator==(const Vec_3d& o) const { return x == o.x && y == o.y && z == o.z; }
+    NEON_CUDA_HOST_DEVICE constexpr bool operator!=(const Vec_3d& o) const { return !(*this == o); }
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d operator+(const Vec_3d& o) const { return {T(x + o.x), T(y + o.y), T(z + o.z)}; }
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d operator-(const Vec_3d& o) const { return {T(x - o.x), T(y - o.y), T(z - o.z)}; }
+    NEON_CUDA_HOST_DEVICE constexpr Vec_3d operator-() const { return {T(-x), T(-y), T(-z)}; }
     template <typename K = size_t>
-    constexpr K rMul() const
+    NEON_CUDA_HOST_DEVICE constexpr K rMul() const
     {
         return K(x) * K(y) * K(z);
     }
@@ -60,6 +71,7 @@ struct Vec_3d
 };
 using index_3d = Vec_3d<int32_t>;
 using int32_3d = Vec_3d<int32_t>;
+using int8_3d = Vec_3d<int8_t>;
 using double_3d = Vec_3d<double>;
 using float_3d = Vec_3d<float>;
 

@@ -382,14 +382,8 @@ class bField
     const index_3d&    getDimension() const { return mS->grid.getDimension(); }
     const Backend&     getBackend() const { return mS->grid.getBackend(); }
     bool               isValid() const { return bool(mS); }
-    Partition          getPartition(int setIdx) const
-    {
-        Partition p;
-        p.memory = static_cast<DeviceType*>(mS->dev.at(setIdx));
-        p.desc = mS->grid.descOf(setIdx);
-        p.card = mS->cardinality;
-        return p;
-    }
+    Partition&         getPartition(int setIdx) { return mS->parts.at(setIdx); }
+    const Partition&   getPartition(int setIdx) const { return mS->parts.at(setIdx); }
 
     T& getReference(const index_3d& p, int card)
     {
@@ -502,6 +496,7 @@ class bField
         uint64_t            uid = 0;
         std::vector<T>      host;
         std::vector<void*>  dev;
+        std::vector<Partition> parts;
         std::vector<DeviceType*> staging; /* pinned [cardinality][nAlloc][512] per partition */
         ~State()
         {
@@ -544,6 +539,11 @@ class bField
             }
             s.dev.push_back(p);
             s.staging.push_back(st);
+            Partition part;
+            part.memory = static_cast<DeviceType*>(p);
+            part.desc = grid.descOf(d);
+            part.card = cardinality;
+            s.parts.push_back(part);
         }
     }
 

@@ -60,10 +60,48 @@ struct FlagWordCodec
 
 }  // namespace Neon::domain
 
+namespace Neon::domain {
+/* Neon::domain::NghData (interface/NghData.h:9-49): value of a neighbour cell + whether that neighbour exists */
+template <typename T>
+struct NghData
+{
+    T    mData;
+    bool mIsValid;
+    NEON_CUDA_HOST_DEVICE T    operator()() const { return mData; }
+    NEON_CUDA_HOST_DEVICE T    getData() const { return mData; }
+    NEON_CUDA_HOST_DEVICE bool isValid() const { return mIsValid; }
+};
+}  // namespace Neon::domain
+
 namespace Neon {
 
 template <typename T, int C>
 class dField;
+
+/* cell handle inside a partition: x, y and the LOCAL z (dIndex.h) */
+struct dIdx
+{
+    int32_t x = 0, y = 0, z = 0;
+};
+
+/* which cells of a partition one launch visits (dSpan.h:45-48, dSpan_imp.h:6-43): STANDARD all local planes, INTERNAL
+ * [r, nz-r), BOUNDARY [0,r) U [nz-r,nz) with r = z_halo (the reference's BOUNDARY fold is not reproduced) */
+struct dSpan
+{
+    using Idx = dIdx;
+    int32_t nx = 0, ny = 0, nzLocal = 0, r = 0, nzView = 0;
+    int32_t view = 0;
+    NEON_CUDA_HOST_DEVICE bool setAndValidate(dIdx& idx, int x, int y, int z) const
+    {
+        if (x >= nx || y >= ny || z >= nzView) {
+            return false;
+        }
+        idx.x = x;
+        idx.y = y;
+        idx.z = view == int(DataView::STANDARD) ? z : view == int(DataView::INTERNAL) ? z + r : (z < r ? z : nzLocal - 2 * r + z);
+        return true;
+    }
+};
 
 namespace detail {
 
@@ -196,6 +234,27 @@ class dGrid
         return dField<T, C>(*this, name, cardinality, outsideValue, mS->nextUid++);
     }
 
+    using Span = dSpan;
+    using Idx = dIdx;
+    dSpan getSpan(int setIdx, DataView dataView) const
+    {
+        dSpan sp;
+        sp.nx = mS->dim.x;
+        sp.ny = mS->dim.y;
+        sp.nzLocal = mS->nzLocal.at(setIdx);
+        sp.r = mS->zHalo;
+        sp.view = int(dataView);
+        const int internal = std::max(0, sp.nzLocal - 2 * sp.r);
+        sp.nzView = dataView == DataView::STANDARD ? sp.nzLocal : dataView == DataView::INTERNAL ? internal : sp.nzLocal - internal;
+        return sp;
+    }
+
+    /* Grid::newContainer(name, loadingLambda): a container whose body is a per-cell device lambda, launched by a
+     * generic kernel over the span of the data view (DeviceContainer.h:88-111, LambdaExecutor.h:12-39).  Needs nvcc with
+     * --extended-lambda: include "Neon/domain/GenericContainer.h" from a .cu translation unit. */
+    template <typename LoadingLambda>
+    set::Container newContainer(const std::string& name, LoadingLambda loadingLambda) const;
+
    private:
     std::shared_ptr<detail::dGridState> mS;
 };
@@ -315,19 +374,61 @@ class dField
     using Grid = dGrid;
     using DeviceType = std::conditional_t<kFlagWords, uint32_t, T>;
 
-    /* what a launcher gets from Loader::load: the device memory of the field on one device and its layout
-     * (the reference's dPartition, dPartition.h:423-434, without the per-cell accessors the C ABI replaces) */
+    /* What Loader::load returns: the device memory of the field on one device and its layout — the reference's
+     * dPartition (dPartition.h:423-434).  The LBM containers hand `mem()` and `desc` to the C ABI; generic per-cell
+     * lambdas (dGrid::newContainer, compiled by nvcc) use the accessors: operator()(idx, card), getNghData<dx,dy,dz>
+     * (dPartition.h:174-207, 265-299), getGlobalIndex.  A flag-word field exposes the packed 32-bit words. */
     struct Partition
     {
+        using Idx = dIdx;
+        using Type = DeviceType;
         DeviceType*     memory = nullptr;
         nlbm_dense_desc desc{};
         int             card = 0;
-        DeviceType*     mem() const { return memory; }
-        index_3d        dim() const { return {desc.nx, desc.ny, desc.nz_local}; }
-        index_3d        origin() const { return {0, 0, desc.z_origin}; }
-        int             zHalo() const { return desc.z_halo; }
-        int             cardinality() const { return card; }
+        DeviceType      outsideValue{};
+
+        NEON_CUDA_HOST_DEVICE DeviceType* mem() const { return memory; }
+        NEON_CUDA_HOST_DEVICE index_3d    dim() const { return {desc.nx, desc.ny, desc.nz_local}; }
+        NEON_CUDA_HOST_DEVICE index_3d    origin() const { return {0, 0, desc.z_origin}; }
+        NEON_CUDA_HOST_DEVICE int         zHalo() const { return desc.z_halo; }
+        NEON_CUDA_HOST_DEVICE int         cardinality() const { return card; }
+
+        NEON_CUDA_HOST_DEVICE int64_t offset(int x, int y, int zLocal, int c) const
+        {
+            return int64_t(c) * desc.pitch_q + int64_t(zLocal + desc.z_halo) * desc.pitch_z + int64_t(y) * desc.pitch_y + x;
+        }
+        NEON_CUDA_HOST_DEVICE DeviceType& operator()(const dIdx& i, int c) const { return memory[offset(i.x, i.y, i.z, c)]; }
+        NEON_CUDA_HOST_DEVICE index_3d    getGlobalIndex(const dIdx& i) const { return {i.x, i.y, i.z + desc.z_origin}; }
+        /* a neighbour is valid when it lies inside the global box (its plane is then local or a ghost plane) */
+        NEON_CUDA_HOST_DEVICE bool isNghValid(const dIdx& i, int dx, int dy, int dz) const
+        {
+            const int x = i.x + dx, y = i.y + dy, gz = i.z + dz + desc.z_origin, lz = i.z + dz;
+            return x >= 0 && x < desc.nx && y >= 0 && y < desc.ny && gz >= 0 && gz < desc.gnz && lz >= -desc.z_halo &&
+                   lz < desc.nz_local + desc.z_halo;
+        }
+        NEON_CUDA_HOST_DEVICE domain::NghData<DeviceType> getNghData(const dIdx& i, const index_3d& off, int c) const
+        {
+            domain::NghData<DeviceType> r;
+            r.mIsValid = isNghValid(i, off.x, off.y, off.z);
+            if (r.mIsValid) {
+                r.mData = memory[offset(i.x + off.x, i.y + off.y, i.z + off.z, c)];
+            } else {
+                r.mData = outsideValue;
+            }
+            return r;
+        }
+        template <int dx, int dy, int dz>
+        NEON_CUDA_HOST_DEVICE domain::NghData<DeviceType> getNghData(const dIdx& i, int c) const
+        {
+            return getNghData(i, index_3d(dx, dy, dz), c);
+        }
+        template <int dx, int dy, int dz>
+        NEON_CUDA_HOST_DEVICE DeviceType getNghData(const dIdx& i, int c, DeviceType alternative) const
+        {
+            return isNghValid(i, dx, dy, dz) ? memory[offset(i.x + dx, i.y + dy, i.z + dz, c)] : alternative;
+        }
     };
+    using Idx = dIdx;
 
     dField() = default;
 
@@ -337,14 +438,8 @@ class dField
     const dGrid&       getGrid() const { return mS->grid; }
     const index_3d&    getDimension() const { return mS->grid.getDimension(); }
     const Backend&     getBackend() const { return mS->grid.getBackend(); }
-    Partition          getPartition(int setIdx) const
-    {
-        Partition p;
-        p.memory = static_cast<DeviceType*>(mS->dev.at(setIdx));
-        p.desc = mS->grid.descOf(setIdx);
-        p.card = mS->cardinality;
-        return p;
-    }
+    Partition&         getPartition(int setIdx) { return mS->parts.at(setIdx); }
+    const Partition&   getPartition(int setIdx) const { return mS->parts.at(setIdx); }
     bool isValid() const { return bool(mS); }
 
     // ---- host mirror ---------------------------------------------------------------------------------------------
@@ -514,6 +609,7 @@ class dField
         T*                    host = nullptr;
         bool                  hostPinned = false;
         std::vector<void*>    dev;      /* per partition */
+        std::vector<Partition> parts;   /* per partition: what Loader::load hands out */
         std::vector<size_t>   devBytes; /* per partition */
         std::vector<uint32_t*> staging; /* flag-word fields: pinned [zm][y][pitch] words per partition */
         ~State()
@@ -580,6 +676,16 @@ class dField
             }
             s.dev.push_back(p);
             s.devBytes.push_back(bytes);
+            Partition part;
+            part.memory = static_cast<DeviceType*>(p);
+            part.desc = desc;
+            part.card = cardinality;
+            if constexpr (kFlagWords) {
+                part.outsideValue = Codec::pack(outside);
+            } else {
+                part.outsideValue = outside;
+            }
+            s.parts.push_back(part);
             if constexpr (kFlagWords) {
                 uint32_t* st = nullptr;
                 if (cuda) {

@@ -129,8 +129,9 @@ class Loader
     Loader(int setIdx, std::vector<Token>* tokens) : mSetIdx(setIdx), mTokens(tokens) {}
 
     template <typename Field>
-    auto load(Field& field, Pattern pattern = Pattern::MAP, StencilSemantic semantic = StencilSemantic::standard) ->
-        typename std::remove_const_t<Field>::Partition
+    auto load(Field& field, Pattern pattern = Pattern::MAP, StencilSemantic semantic = StencilSemantic::standard)
+        -> std::conditional_t<std::is_const_v<Field>, const typename std::remove_const_t<Field>::Partition&,
+                              typename std::remove_const_t<Field>::Partition&>
     {
         constexpr bool isConst = std::is_const_v<Field>;
         if (mTokens && mSetIdx == 0) {

@@ -214,3 +214,27 @@ def test_two_real_devices_one_process(app, tmp_path, oracle, grid, extra):
     d = _dump_grid(app, str(tmp_path), grid, dim, "float", "sphere", iters, extra=extra, devices=(0, 1))
     assert np.array_equal(d["mask"], mask)
     assert np.array_equal(d["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+# ------------------------------------------------------------------------------------------- generic lambda containers
+GEN = os.path.join(CPP, "bin", "generic-containers")
+
+
+def test_generic_container_app_builds_with_the_generic_kernel(app):
+    """Grid::newContainer(name, loadingLambda) instantiates the generic span kernel for every user lambda (nvcc)"""
+    assert os.path.exists(GEN)
+    sass = subprocess.run(["cuobjdump", "-sass", GEN], capture_output=True, text=True).stdout
+    assert sass.count("neonLambdaOnSpan") >= 3 and "sm_100a" in sass
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", [(0,), (0, 0), (0, 0, 0, 0), (0, 1)])
+def test_generic_lambda_containers(app, tmp_path, devices):
+    """user-written MAP / STENCIL / LBM device lambdas through newContainer + Skeleton (OCC, halo updates) on 1-4 partitions"""
+    torch = pytest.importorskip("torch")
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip("needs two GPUs")
+    r = subprocess.run([GEN, "--deviceIds", *[str(d) for d in devices], "--n", "36"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith(("PASS", "FAIL"))]
+    assert len(lines) == 7 and all(l.startswith("PASS") for l in lines), r.stdout

@@ -231,8 +231,9 @@ class FlagField(_FieldBase):
         nx, ny, nz = g.dim
         assert cls_global.shape[1:] == (ny, nx) and host_z0 + cls_global.shape[0] <= nz, cls_global.shape
         host = np.full((g.nzm, ny, self.pitch_y), capi.UNDEFINED << capi.FLAG_CLASS_SHIFT, np.uint32)
-        for zm, gz in self._global_planes():
-            host[zm, :, :nx] = cls_global[gz - host_z0].astype(np.uint32) << capi.FLAG_CLASS_SHIFT
+        planes = self._global_planes()  # consecutive memory planes <-> consecutive global planes
+        (zm0, gz0), n = planes[0], len(planes)
+        np.left_shift(cls_global[gz0 - host_z0:gz0 - host_z0 + n], capi.FLAG_CLASS_SHIFT, out=host[zm0:zm0 + n, :, :nx], casting="unsafe")
         self.cells.copy_(torch.from_numpy(host.view(np.int32)))
         if g.backend.runtime == Runtime.stream:
             capi.call("nlbm_dense_flags_commit", C.byref(self._d()), g.backend.streamHandle(stream_idx))

@@ -66,6 +66,22 @@ def test_fails_loudly_without_a_device(app, tmp_path):
     assert r.returncode == 1 and "NeonException" in r.stderr and "no CPU fallback" in r.stderr
 
 
+def test_host_logic_of_the_veneer(app):
+    """partition rule, spans per data view, Skeleton schedules (Occ none/standard), Loader tokens, CellType codec, bGrid blocks and
+    ghost layers, report writer, refusal to compute without Runtime::stream — neon_b200/cpp/apps/host-logic (no GPU needed)"""
+    r = subprocess.run([os.path.join(CPP, "bin", "host-logic")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
+
+
+def test_sweep_driver_enumerates_the_reference_matrix():
+    """sweep.py reproduces the reference sweep's axes (lbm-lid-driven-cavity-flow.py:1-10) minus cpu / eGrid"""
+    sweep = os.path.join(CPP, "apps", "lbm-lid-driven-cavity-flow", "sweep.py")
+    out = subprocess.run(["python", sweep, "--dry-run", "--gpus", "2"], capture_output=True, text=True, timeout=60).stdout
+    assert "'n': 512" in out and "'grid': 'bGrid'" in out and "'devs': '0 1'" in out
+    assert "'store': 'double', 'compute': 'float'" not in out
+    assert int(out.strip().splitlines()[-1].split()[0]) == 8 * (3 * 2 + 2 * 2)  # sizes x (dGrid: 3 pairs x 2 device sets + bGrid: 2 x 2)
+
+
 # ------------------------------------------------------------------------------------------------------------ GPU
 GOLDEN = [  # name, dim, fp, geom
     ("cavity16_f32", (16, 16, 16), "float", "cavity"),

@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--rows-log2", type=int, default=0)
     ap.add_argument("--flags-summary-first", action="store_true")
     ap.add_argument("--rpw", type=int, default=0, help="rows per warp selector: 0 default, else log2(rows)+1")
+    ap.add_argument("--experiment", type=int, default=0, help="MEASUREMENT ONLY (wrong results): 1 no flags/walls, 2 no edge loads, 3 both")
+    ap.add_argument("--no-xface-prefetch", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")
@@ -249,7 +251,7 @@ def main():
     omega = wl.get("omega", nb.omega_from_re(dim[0]))
     arith = nb.ARITH_FAST if args.arith == "fast" else nb.ARITH_REFERENCE
     opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[args.kernel]) \
-        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0) | ((args.rpw & 7) << 21)
+        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0) | ((args.rpw & 7) << 21) | ((args.experiment & 7) << 24) | ((1 << 27) if args.no_xface_prefetch else 0)
     occ = nb.Occ.standard if args.occ == "standard" else nb.Occ.none
 
     bk = nb.Backend()
@@ -393,7 +395,7 @@ def main():
         line = {"metric": f"LBM MLUPS (D3Q{q} {'fp32' if dtype.itemsize == 4 else 'fp64'})", "value": mlups, "unit": "MLUPS",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32" if dtype.itemsize == 4 else "f64", "data": "synthetic",
-                "config": {"workload": wl["name"], "dim": list(dim), "lattice": f"D3Q{q}", "arith": args.arith, "kernel": args.kernel,
+                "config": {"workload": wl["name"], "dim": list(dim), "lattice": f"D3Q{q}", "arith": args.arith, "kernel": args.kernel, **({"EXPERIMENT_wrong_results": args.experiment} if args.experiment else {}),
                            "occ": args.occ if world > 1 else "n/a (1 partition)", "halo_transport": args.transport if world > 1 else "n/a",
                            "l2": "inputs exceed L2 (two population fields of %.1f GB per GPU)" % (q * cells_rank * dtype.itemsize / 1e9),
                            "partition": (f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes") if world > 1 else "single partition"},

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NLBM_ABI_VERSION 1
+#define NLBM_ABI_VERSION 2
 
 typedef enum nlbm_status {
     NLBM_OK = 0,
@@ -88,6 +88,14 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 /* bits 21..23 (direct kernel): rows a warp covers, 0 = library default, else log2(rows) + 1 (1: whole-row warps of 32 lanes,
  * 3: 4 rows x 8 lanes ...).  Narrow warp tiles keep the wall round trip away from most warps.  Never changes results.      */
 #define NLBM_OPT_ROWS_PER_WARP_LOG2P1(r) (((r)&0x7) << 21)
+/* bits 24..26 (direct kernel): MEASUREMENT ONLY — the results are WRONG.  Value 1: every in-box cell is treated as plain
+ * bulk and no flag word is loaded (what the streaming part alone reaches); value 2: the flag words are loaded but ignored;
+ * value 3: flags are honoured but wall fix-ups and kept wall values are skipped.  Used by bench.py --experiment to attribute the gap to the roofline; never set by the host layers.          */
+#define NLBM_OPT_EXPERIMENT(e) (((e)&0x7) << 24)
+/* bit 27 (direct kernel): do not fetch the output-field values of the cells on the x faces of the box speculatively (default:
+ * fetch them with the streaming loads — the kept wall values of those cells are then no dependent DRAM round trip).  Never
+ * changes results.                                                                                                      */
+#define NLBM_OPT_NO_XFACE_PREFETCH (1 << 27)
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2
@@ -116,6 +124,9 @@ typedef struct nlbm_dense_desc {
     int64_t   pitch_y, pitch_z, pitch_q; /* in elements                               */
     int32_t   z_origin;         /* global z of local plane 0                          */
     int32_t   gnx, gny, gnz;    /* global box                                         */
+    void*     wall_cache;       /* device, borrowed, may be NULL: x-face cache of the field in pop_out
+                                   (nlbm_dense_wall_cache_build); lets the step kernels keep wall values
+                                   of the cells at x = 0 and x = nx-1 without touching their rows   */
 } nlbm_dense_desc;
 
 int         nlbm_abi_version(void);
@@ -128,6 +139,18 @@ int nlbm_device_count(void);
  * needs in *pop_bytes and the flag array in *flag_bytes.  Host only.  This is where
  * the reference decides its pitch: dField_imp.h:67-87.                            */
 int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_bytes, size_t* flag_bytes);
+
+/* ---- x-face cache of a population field (optional, an optimisation of the step kernels) -----------------------------
+ * Non-bulk cells are never updated (LbmTools.h:304), yet the thread that owns a wall cell at x = 0 or x = nx-1 together
+ * with bulk cells stores 16 bytes per population and has to put the wall cell's present value of the OUTPUT field back.
+ * Reading that value from its row costs one isolated DRAM access (a row activation) per row, population and side — as
+ * many activations again as the whole streaming sweep (measured: 6-8 % of the iteration).  The cache holds those values
+ * contiguously: cache[side][q][zm][y] = field[q][zm][y][side ? nx-1 : 0].  It stays valid as long as nobody but the step
+ * kernels writes the field: build it once after the field was initialised / uploaded, rebuild it after any other write.
+ * d->pop_out = the field, d->wall_cache = its cache (bytes from nlbm_dense_wall_cache_layout, 128-byte aligned).
+ * With d->wall_cache == NULL in a step call the kernel reads the field itself: same results, slower.                  */
+int nlbm_dense_wall_cache_layout(const nlbm_dense_desc* d, int q, int elem_bytes, size_t* bytes);
+int nlbm_dense_wall_cache_build(const nlbm_dense_desc* d, int q, int elem_bytes, void* stream);
 
 /* ---- problem set-up on the device (RunCavityTwoPop.cu:159-242) ------------------
  * geom: 0 lid-driven cavity; 1 cavity + solid sphere; 2 flow over sphere (x=0 inlet

@@ -55,6 +55,7 @@ class DenseDesc(C.Structure):
         ("nx", C.c_int32), ("ny", C.c_int32), ("nz_local", C.c_int32), ("z_halo", C.c_int32),
         ("pitch_y", C.c_int64), ("pitch_z", C.c_int64), ("pitch_q", C.c_int64),
         ("z_origin", C.c_int32), ("gnx", C.c_int32), ("gny", C.c_int32), ("gnz", C.c_int32),
+        ("wall_cache", C.c_void_p),
     ]
 
     def clone(self) -> "DenseDesc":
@@ -93,6 +94,8 @@ _SIGNATURES = {
     "nlbm_last_error": (C.c_char_p, []),
     "nlbm_device_count": (C.c_int, []),
     "nlbm_dense_layout": (C.c_int, [_D, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "nlbm_dense_wall_cache_layout": (C.c_int, [_D, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "nlbm_dense_wall_cache_build": (C.c_int, [_D, C.c_int, C.c_int, _P]),
     "nlbm_dense_classify": (C.c_int, [_D, C.c_int, C.POINTER(C.c_double), _P]),
     "nlbm_dense_flags_commit": (C.c_int, [_D, _P]),
     "nlbm_dense_wall_mask": (C.c_int, [_D, C.c_int, _P, _P]),

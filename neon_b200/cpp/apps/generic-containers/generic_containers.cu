@@ -222,6 +222,9 @@ void testLbm(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, int benchI
             Neon::detail::check(nlbm_dense_init_pop_f32(&desc, 19, 0.04, st), "init");
         }
     }
+    for (Pop* f : {&a0, &a1, &b0, &b1}) {
+        f->commitWalls(); /* a0/a1 lose theirs again as soon as the user lambda writes them; b0/b1 keep it for the native kernel */
+    }
     bk.syncAll();
     const auto               sem = Neon::set::StencilSemantic::streaming;
     Neon::skeleton::Skeleton user[2] = {Neon::skeleton::Skeleton(bk), Neon::skeleton::Skeleton(bk)};

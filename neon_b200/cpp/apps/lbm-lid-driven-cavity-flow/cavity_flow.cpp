@@ -362,6 +362,8 @@ void run(Config& config, RunReport& report)
                 }
             }
         }
+        pop0.commitWalls();
+        pop1.commitWalls();
         bk.syncAll();
     } else {
         iteration.getInput().forEachActiveCell(initPop);

@@ -58,6 +58,7 @@ set::Container dGrid::newContainer(const std::string& name, LoadingLambda loadin
     auto impl = std::make_shared<set::detail::DeviceManagedImpl>();
     impl->name = name;
     impl->backend = getBackend();
+    impl->genericBody = true;
     const Backend bk = getBackend();
     const dGrid   grid = *this;
     for (int d = 0; d < bk.getDeviceCount(); ++d) {

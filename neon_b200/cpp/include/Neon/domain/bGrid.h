@@ -444,6 +444,10 @@ class bField
     }
 
     void updateDeviceData(int streamIdx = Backend::mainStreamIdx) { transfer(streamIdx, true); }
+    /* block-sparse fields have no x-face cache (dField::commitWalls); same calls so that code is generic over the grid */
+    void  commitWalls(int = Backend::mainStreamIdx) {}
+    void  invalidateWalls() const {}
+    void* wallCachePtr(int) const { return nullptr; }
     void updateHostData(int streamIdx = Backend::mainStreamIdx) { transfer(streamIdx, false); }
 
     set::Container newHaloUpdate(set::StencilSemantic semantic, set::TransferMode mode, Execution execution = Execution::device) const

@@ -509,10 +509,35 @@ class dField
                                                      mode);
     }
 
+    // ---- x-face cache (include/neon_lbm.h): the LBM step keeps wall values of the cells at x = 0 / nx-1 from it.  Every
+    // writer of this class refreshes it (updateDeviceData); whoever writes the device memory otherwise (set-up kernels,
+    // generic containers) calls commitWalls() afterwards — generic containers invalidate it when they run.
+    void commitWalls(int streamIdx = Backend::mainStreamIdx)
+    {
+        if constexpr (!kFlagWords) {
+            const Backend& bk = getBackend();
+            if (bk.runtime() != Runtime::stream) {
+                return;
+            }
+            for (int d = 0; d < mS->grid.getNumPartitions(); ++d) {
+                bk.setDevice(d);
+                nlbm_dense_desc desc = mS->grid.descOf(d);
+                desc.pop_out = mS->dev[d];
+                desc.wall_cache = mS->wallCache[d];
+                detail::check(nlbm_dense_wall_cache_build(&desc, mS->cardinality, int(sizeof(T)), bk.stream(d, streamIdx)),
+                              "nlbm_dense_wall_cache_build");
+            }
+            mS->wallsCommitted = true;
+        }
+    }
+    void  invalidateWalls() const { mS->wallsCommitted = false; }
+    void* wallCachePtr(int setIdx) const { return mS->wallsCommitted ? mS->wallCache.at(setIdx) : nullptr; }
+
     // ---- host <-> device (FieldBase::updateDeviceData / updateHostData), asynchronous on stream `streamIdx` ----------
     void updateDeviceData(int streamIdx = Backend::mainStreamIdx)
     {
         transfer(streamIdx, /*toDevice*/ true);
+        commitWalls(streamIdx);
     }
     void updateHostData(int streamIdx = Backend::mainStreamIdx)
     {
@@ -610,6 +635,8 @@ class dField
         bool                  hostPinned = false;
         std::vector<void*>    dev;      /* per partition */
         std::vector<Partition> parts;   /* per partition: what Loader::load hands out */
+        std::vector<void*>    wallCache; /* per partition: x-face cache of the field (nlbm_dense_wall_cache_build) */
+        bool                  wallsCommitted = false;
         std::vector<size_t>   devBytes; /* per partition */
         std::vector<uint32_t*> staging; /* flag-word fields: pinned [zm][y][pitch] words per partition */
         ~State()
@@ -619,6 +646,12 @@ class dField
                 if (dev[d]) {
                     cudaSetDevice(bk.devId(int(d)));
                     cudaFree(dev[d]);
+                }
+            }
+            for (size_t d = 0; d < wallCache.size(); ++d) {
+                if (wallCache[d]) {
+                    cudaSetDevice(bk.devId(int(d)));
+                    cudaFree(wallCache[d]);
                 }
             }
             for (auto* p : staging) {
@@ -686,6 +719,15 @@ class dField
                 part.outsideValue = outside;
             }
             s.parts.push_back(part);
+            void* wc = nullptr;
+            if constexpr (!kFlagWords) {
+                if (cuda) {
+                    size_t wcBytes = 0;
+                    detail::check(nlbm_dense_wall_cache_layout(&desc, cardinality, int(sizeof(T)), &wcBytes), "nlbm_dense_wall_cache_layout");
+                    NEON_CUDA_CHECK(cudaMalloc(&wc, wcBytes));
+                }
+            }
+            s.wallCache.push_back(wc);
             if constexpr (kFlagWords) {
                 uint32_t* st = nullptr;
                 if (cuda) {

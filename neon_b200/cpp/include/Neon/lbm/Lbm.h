@@ -207,9 +207,14 @@ struct LbmContainers
                 d.pop_in = fIn.mem();
                 d.pop_out = fOut.mem();
                 d.flags = flg.mem();
-                const int dev = setIdx.idx;
+                const int             dev = setIdx.idx;
+                const PopulationField outHandle = fOutField; /* shallow handle: its x-face cache may be (in)validated later */
                 return [=](int streamIdx, Neon::DataView dataView) {
-                    Neon::detail::check(step(&d, om, static_cast<int>(dataView), opts, bk.stream(dev, streamIdx)), "nlbm step");
+                    Desc dd = d;
+                    if constexpr (!isBlock) {
+                        dd.wall_cache = outHandle.wallCachePtr(dev);
+                    }
+                    Neon::detail::check(step(&dd, om, static_cast<int>(dataView), opts, bk.stream(dev, streamIdx)), "nlbm step");
                 };
             });
     }

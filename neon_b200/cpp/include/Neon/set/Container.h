@@ -54,6 +54,9 @@ struct Token
     StencilSemantic semantic = StencilSemantic::standard;
     /* builds the halo-update container of the field (FieldBase::newHaloUpdate) — only set for stencil reads */
     std::function<Container(StencilSemantic, TransferMode, Execution)> newHaloUpdate;
+    /* set for writes: tells the field that a container with an arbitrary body is about to write it (derived data the
+     * library keeps about the field, e.g. dField's x-face cache, is then stale) */
+    std::function<void()> onGenericWrite;
 };
 
 class Loader;
@@ -145,6 +148,10 @@ class Loader
                 auto copy = field; /* fields are shallow handles (dField.h:150-195) */
                 t.newHaloUpdate = [copy](StencilSemantic s, TransferMode m, Execution e) { return copy.newHaloUpdate(s, m, e); };
             }
+            if (!isConst) {
+                auto copy = field;
+                t.onGenericWrite = [copy]() { copy.invalidateWalls(); };
+            }
             mTokens->push_back(std::move(t));
         }
         return field.getPartition(mSetIdx);
@@ -160,8 +167,16 @@ namespace detail {
 struct DeviceManagedImpl : Container::Impl
 {
     std::vector<std::function<void(int, DataView)>> launchers; /* one per device */
+    bool                                            genericBody = false; /* user lambda: may write anything it loaded non-const */
     void run(int streamIdx, DataView dataView) override
     {
+        if (genericBody) {
+            for (const auto& t : tokens) {
+                if (t.access == Access::write && t.onGenericWrite) {
+                    t.onGenericWrite();
+                }
+            }
+        }
         for (int d = 0; d < int(launchers.size()); ++d) {
             run(d, streamIdx, dataView);
         }

@@ -153,6 +153,11 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
     a.omega = omega;
     a.flagsAlways = ((opts >> 20) & 1) ? 0 : 1;
+    a.prefetchXFaces = ((opts >> 27) & 1) ? 0 : 1;  // NLBM_OPT_NO_XFACE_PREFETCH
+    a.keepCache = d->wall_cache;
+    a.experiment = (opts >> 24) & 0x7;  // NLBM_OPT_EXPERIMENT: measurement only
+    if (a.experiment)
+        a.flagsAlways = 1;
     a.lprLog2 = 5;
     a.peerMode = 0;
     a.nzLocal = d->nz_local;
@@ -308,6 +313,23 @@ int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_byt
         *flag_bytes = (size_t)(nlbm::flagCellWords(*d) + 2 * rows * nlbm::summaryWordsPerRow(d->pitch_y)) * 4;
     }
     return NLBM_OK;
+}
+
+int nlbm_dense_wall_cache_layout(const nlbm_dense_desc* d, int q, int elem_bytes, size_t* bytes)
+{
+    if (!d || !bytes || d->ny <= 0 || d->nz_local <= 0 || d->z_halo < 0 || d->z_halo > 1 || q < 1 || q > 27 || (elem_bytes != 4 && elem_bytes != 8))
+        return fail(NLBM_ERR_INVALID, "bad wall-cache request");
+    *bytes = (size_t)nlbm::alignUp((int64_t)2 * q * (d->nz_local + 2 * d->z_halo) * d->ny * elem_bytes, 128);
+    return NLBM_OK;
+}
+int nlbm_dense_wall_cache_build(const nlbm_dense_desc* d, int q, int elem_bytes, void* stream)
+{
+    if (int rc = checkDesc(d, elem_bytes, false, true, false))
+        return rc;
+    if (!d->wall_cache || ((uintptr_t)d->wall_cache & 127) || q < 1 || q > 27 || (elem_bytes != 4 && elem_bytes != 8))
+        return fail(NLBM_ERR_INVALID, "wall cache null / misaligned, or bad component count / element size");
+    cudaError_t e = nlbm::launchWallCacheBuild(*d, q, elem_bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "wall cache build launch");
 }
 
 int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream)

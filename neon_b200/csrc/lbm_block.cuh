@@ -137,21 +137,18 @@ __device__ __forceinline__ void blockFixLoad(const T* __restrict__ popIn, const 
 {
     constexpr int q = Pairs<L>::lo(P), o = L::opp(q);
     const bool    bq = (m >> q) & 1u, bo = (m >> o) & 1u;
-    tb = T(0);
-    if (bq | bo) {
-        // bq: f_o(x) + f_o(x - c_q);   bo (only): f_q(x) + f_q(x + c_q)
-        const int  s = bq ? -1 : 1;
-        const int  xn = x + s * L::c(q, 0), yn = y + s * L::c(q, 1), zn = z + s * L::c(q, 2);
-        const int  fx = (xn < 0) ? -1 : (xn >= kB ? 1 : 0), fy = (yn < 0) ? -1 : (yn >= kB ? 1 : 0), fz = (zn < 0) ? -1 : (zn >= kB ? 1 : 0);
-        const uint32_t bn = (fx | fy | fz) ? nbr[(fx + 1) + 3 * (fy + 1) + 9 * (fz + 1)] : blk;
-        const T*   plane = popIn + (bq ? o : q) * a.popPitch;
-        const T    first = __ldg(plane + (int64_t)blk * kBlockCells + (z * (kB * kB) + y * kB + x));
-        tb = bn != kNoBlock ? __ldg(plane + (int64_t)bn * kBlockCells + ((zn - fz * kB) * (kB * kB) + (yn - fy * kB) * kB + (xn - fx * kB))) : T(0);
-        if (bq)
-            f[q][i] = first;
-        else
-            f[o][i] = first;
-    }
+    // bq: f_o(x) + f_o(x - c_q);   bo (only): f_q(x) + f_q(x + c_q).  Predicated volatile PTX loads without a consumer here, the
+    // first operand straight into the slot it replaces (see fixLoad in lbm_step.cuh: selects behind plain loads serialised the pairs)
+    const int      s = bq ? -1 : 1;
+    const int      xn = x + s * L::c(q, 0), yn = y + s * L::c(q, 1), zn = z + s * L::c(q, 2);
+    const int      fx = (xn < 0) ? -1 : (xn >= kB ? 1 : 0), fy = (yn < 0) ? -1 : (yn >= kB ? 1 : 0), fz = (zn < 0) ? -1 : (zn >= kB ? 1 : 0);
+    const uint32_t bn = (fx | fy | fz) ? nbr[(fx + 1) + 3 * (fy + 1) + 9 * (fz + 1)] : blk;
+    const T*       plane = popIn + (bq ? o : q) * a.popPitch;
+    const T*       own = plane + (int64_t)blk * kBlockCells + (z * (kB * kB) + y * kB + x);
+    const T*       ngh = plane + (int64_t)bn * kBlockCells + ((zn - fz * kB) * (kB * kB) + (yn - fy * kB) * kB + (xn - fx * kB));
+    f[q][i] = ldPredKeepNc1(own, bq, f[q][i]);
+    f[o][i] = ldPredKeepNc1(own, bo && !bq, f[o][i]);
+    tb = ldPred1(ngh, (bq || bo) && bn != kNoBlock);
 }
 template <class L, typename T, int VEC, int P>
 __device__ __forceinline__ void blockFixUse(const T* __restrict__ popIn, const BlockArgs& a, const uint32_t blk, const uint32_t* __restrict__ nbr,

@@ -99,6 +99,9 @@ struct DenseArgs
     int32_t fold, skip;   // view planes >= fold are shifted by skip (BOUNDARY view: two slabs)
     int32_t lprLog2;      // direct kernel: log2 of the lanes a warp spends on one row (32 = whole-row warps)
     int32_t flagsAlways;  // direct kernel: fetch the flag words with the populations instead of consulting the row summary first
+    int32_t prefetchXFaces;  // direct kernel: fetch the output-field values of the cells at x = 0 and x = nx-1 speculatively (cp.async)
+    const void* keepCache;   // x-face cache of the output field (nlbm_dense_wall_cache_build) or null
+    int32_t experiment;   // MEASUREMENT ONLY (results are wrong): 1 every cell is plain bulk, no flag loads; 2 flags loaded but ignored
     double  omega;
     // ---- fused face push (nlbm_dense_step_push): the kernel stores the crossing populations of its two z-boundary planes
     // straight into the z-neighbours' ghost planes and signals them; all null / 0 for the plain step
@@ -202,6 +205,28 @@ __device__ __forceinline__ double ldPredCoherent1(const double* p, bool pred, do
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
     return keep;
 }
+// read-only-path variants that leave `keep` untouched when the predicate is false: the loaded value lands in the register
+// it replaces, so no select sits between the load and its (much later) consumer
+__device__ __forceinline__ float ldPredKeepNc1(const float* p, bool pred, float keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f32 %0, [%1];\n}\n" : "+f"(keep) : "l"(p), "r"((uint32_t)pred));
+    return keep;
+}
+__device__ __forceinline__ double ldPredKeepNc1(const double* p, bool pred, double keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
+    return keep;
+}
+// asynchronous copy of one element from global to shared memory: no destination register, nobody waits until cpAsyncWait
+__device__ __forceinline__ void cpAsync1(float* smem, const float* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync1(double* smem, const double* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // flag words of VEC cells; pred == false yields "undefined" cells (never updated)
 template <int VEC>
 __device__ __forceinline__ void ldFlags(const uint32_t* p, bool pred, uint32_t (&v)[VEC])
@@ -237,6 +262,15 @@ __device__ __forceinline__ void ldVec(const T* __restrict__ p, T (&v)[VEC])
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
         v[i] = e[i];
+}
+// one element, streaming, under a predicate (threads that own bulk AND non-bulk cells store their bulk cells one by one)
+__device__ __forceinline__ void stPred1(float* p, const float v, const bool pred)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.cs.f32 [%0], %1;\n}\n" ::"l"(p), "f"(v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void stPred1(double* p, const double v, const bool pred)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.cs.f64 [%0], %1;\n}\n" ::"l"(p), "d"(v), "r"((uint32_t)pred) : "memory");
 }
 template <typename T, int VEC>
 __device__ __forceinline__ void stVec(T* __restrict__ p, const T (&v)[VEC])

@@ -30,6 +30,7 @@ void tmaTileShape(int elemBytes, int nx, int* tx, int* ty);
 
 // lbm_setup.cu
 cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st);
+cudaError_t launchWallCacheBuild(const nlbm_dense_desc& d, int q, int elemBytes, cudaStream_t st);
 cudaError_t launchClassify(const nlbm_dense_desc& d, int geom, const double* sphere, cudaStream_t st);
 cudaError_t launchWallMask(const nlbm_dense_desc& d, int q, int32_t* d_bad, cudaStream_t st);
 template <typename S>

@@ -238,6 +238,37 @@ static GeomArgs geomArgs(const nlbm_dense_desc& d, int geom, const double* spher
     return g;
 }
 
+// x-face cache of a field: cache[side][q][zm][y] = field[q][zm][y][side ? nx-1 : 0]   (include/neon_lbm.h)
+template <typename W>
+__global__ void k_wall_cache_build(const W* __restrict__ field, W* __restrict__ cache, int nx, int ny, int nzm, int q, int64_t pitch_y,
+                                   int64_t pitch_z, int64_t pitch_q)
+{
+    const int64_t rows = (int64_t)q * nzm * ny;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * rows)
+        return;
+    const int     side = t >= rows;
+    const int64_t r = t - side * rows;
+    const int     y = (int)(r % ny);
+    const int     zm = (int)((r / ny) % nzm);
+    const int     c = (int)(r / ((int64_t)ny * nzm));
+    cache[t] = field[c * pitch_q + zm * pitch_z + y * pitch_y + (side ? nx - 1 : 0)];
+}
+cudaError_t launchWallCacheBuild(const nlbm_dense_desc& d, int q, int elemBytes, cudaStream_t st)
+{
+    const int     nzm = d.nz_local + 2 * d.z_halo;
+    const int64_t n = (int64_t)2 * q * nzm * d.ny;
+    const int     threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (elemBytes == 4)
+        k_wall_cache_build<uint32_t><<<blocks, threads, 0, st>>>((const uint32_t*)d.pop_out, (uint32_t*)d.wall_cache, d.nx, d.ny, nzm, q,
+                                                                 d.pitch_y, d.pitch_z, d.pitch_q);
+    else
+        k_wall_cache_build<uint64_t><<<blocks, threads, 0, st>>>((const uint64_t*)d.pop_out, (uint64_t*)d.wall_cache, d.nx, d.ny, nzm, q,
+                                                                 d.pitch_y, d.pitch_z, d.pitch_q);
+    return cudaGetLastError();
+}
+
 cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st)
 {
     const int     nzm = d.nz_local + 2 * d.z_halo;

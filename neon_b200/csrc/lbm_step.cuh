@@ -292,19 +292,16 @@ __device__ __forceinline__ void fixLoad(const T* __restrict__ cell, const DenseA
 {
     constexpr int q = Pairs<L>::lo(P), o = L::opp(q);
     const bool    bq = (m >> q) & 1u, bo = (m >> o) & 1u;
-    tb = T(0);
-    if (bq | bo) {
-        // bq: f_o(x) + f_o(x - c_q);   bo (only): f_q(x) + f_q(x - c_o) = f_q(x) + f_q(x + c_q)
-        // the first operand lands in the slot it replaces (what was pulled from the wall cell is never used)
-        const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
-        const T*      src = cell + (bq ? o : q) * a.pitch_q;
-        const T       first = __ldg(src);
-        tb = __ldg(bq ? src - dn : src + dn);
-        if (bq)
-            f[q][i] = first;
-        else
-            f[o][i] = first;
-    }
+    // bq: f_o(x) + f_o(x - c_q);   bo (only): f_q(x) + f_q(x - c_o) = f_q(x) + f_q(x + c_q)
+    // The first operand lands in the slot it replaces (what was pulled from the wall cell is never used); the second in tb.
+    // Predicated volatile PTX loads without a consumer here: with plain loads and `if (bq) f[q][i] = first` ptxas put a
+    // select right behind every pair of loads and the pairs of a cell went to memory one after the other (ncu r01m: five
+    // serialised round trips per x-wall cell, 1.8x the time of the streaming loads).
+    const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
+    const T*      src = cell + (bq ? o : q) * a.pitch_q;
+    f[q][i] = ldPredKeepNc1(src, bq, f[q][i]);
+    f[o][i] = ldPredKeepNc1(src, bo && !bq, f[o][i]);
+    tb = ldPred1(bq ? src - dn : src + dn, bq || bo);
 }
 template <class L, typename T, int VEC, int P>
 __device__ __forceinline__ void fixUse(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i, const T tb,
@@ -353,7 +350,8 @@ __device__ __forceinline__ void fixCell(const T* __restrict__ cell, const DenseA
 template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5)>
 __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
                                             const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC],
-                                            T* __restrict__ peerDst = nullptr, const int64_t peerPitchQ = 0, const int peerDir = 0)
+                                            T* __restrict__ peerDst = nullptr, const int64_t peerPitchQ = 0, const int peerDir = 0,
+                                            const T* sKeep = nullptr, const int specCell = -1)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -368,13 +366,24 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
         // through one 16-byte store per population: the non-bulk cells carry the value the output field already holds,
         // fetched here — together with the wall fix-up operands, one round trip for both — into the slots whose pulled
         // values are never used, and kept through the collision by a select.  Nobody else writes those cells.
+        // (Storing the bulk cells of such threads one by one instead was measured SLOWER on B200, profiles/r01r: partial
+        // sector writes cost more than these loads.)
+        // (A branch per cell, not 4 x Q predicated loads: the instructions a special warp executes are what keeps it
+        // resident — measured.)
         const bool mixed = anyBulk && !allBulk;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            const bool keepOld = mixed && !flagIsBulk(fl[i]);
+            if (mixed && !flagIsBulk(fl[i])) {
+                if (i == specCell) {  // fetched speculatively next to the streaming loads (the kernel's x-face threads)
 #pragma unroll
-            for (int q = 0; q < Q; ++q)
-                f[q][i] = ldPredCoherent1(out0 + q * a.pitch_q + i, keepOld, f[q][i]);
+                    for (int q = 0; q < Q; ++q)
+                        f[q][i] = sKeep[q * kStepThreads];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        f[q][i] = ldPredCoherent1(out0 + q * a.pitch_q + i, true, f[q][i]);
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -473,11 +482,36 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     uint2    s = make_uint2(0u, 0u);
     uint32_t fl[VEC];
     if (a.flagsAlways)
-        ldFlags<VEC>(a.flags + cellOff, rowOk, fl);
+        ldFlags<VEC>(a.flags + cellOff, rowOk && (a.experiment != 1), fl);
     else
         s = ldPredU2(a.summary + row * a.wpr + (chunk0 >> 5));
     T f[Q][VEC], edge[Q];
     loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, tx, lpr, rowOk, f, edge);
+
+    // The two threads of a row that touch the x faces of the box usually own a wall cell next to bulk cells.  Such a thread
+    // keeps the wall cell's values of the OUTPUT field through its 16-byte stores (finishCells); fetched after the flags had
+    // arrived they were a dependent DRAM round trip that held x-wall warps for as long again as the streaming loads (ncu
+    // r01m: 19 % of all stall samples).  Fetch them now, speculatively and without a destination register: cp.async into
+    // this thread's shared-memory slot (same 32-byte sectors, no extra traffic when the guess is right; an L2 prefetch
+    // pulled whole 128-byte lines and cost the streaming part 6 %, profiles/r01s).  Nothing is assumed about the geometry:
+    // a wrong guess is ignored and any other mixed thread loads late as before.
+    extern __shared__ __align__(16) unsigned char sKeepRaw[];
+    T*        sKeep = reinterpret_cast<T*>(sKeepRaw) + (threadIdx.z * blockDim.y + threadIdx.y) * 32 + lane;
+    // (a thread that owns a single cell is never mixed: nothing to keep)
+    const int specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
+    if (specCell >= 0) {
+        // from the field's x-face cache when the caller maintains one (y-contiguous: no isolated DRAM row activations),
+        // else from the wall cell's own rows
+        const T*      w = reinterpret_cast<const T*>(a.out) + cellOff + specCell;
+        int64_t       stride = a.pitch_q;
+        if (a.keepCache != nullptr) {
+            stride = (int64_t)a.nzm * a.ny;
+            w = reinterpret_cast<const T*>(a.keepCache) + (x0 == 0 ? 0 : Q * stride) + (int64_t)zm * a.ny + y;
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            cpAsync1(sKeep + q * kStepThreads, w + q * stride);
+    }
 
     bool special;
     if (a.flagsAlways) {
@@ -513,15 +547,20 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     }
 
     shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, tx, lpr, f, edge);
+    if (specCell >= 0)
+        cpAsyncWait();  // issued with the streaming loads, which have arrived: free
+    if (a.experiment == 3)  // measurement only: flags decide who is updated, but no wall fix-ups and no kept wall values
+        special = false;
 
     if constexpr (PEER) {
         const int fi = pushes ? face : 0;
         T*        peerDst = (pushes && rowOk) ? reinterpret_cast<T*>(a.peer[fi]) + a.peerOff[fi] + (int64_t)y * a.pitch_y + x0 : nullptr;
-        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi], fi == 0 ? -1 : 1);
+        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi], fi == 0 ? -1 : 1,
+                                 sKeep, specCell);
         if (pushes)
             faceArrive(a, face, lane);
     } else {
-        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f);
+        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep, specCell);
     }
 }
 
@@ -572,7 +611,21 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     if (grid.y > 65535)
         return cudaErrorInvalidConfiguration;
     a.warpsPerFace = grid.x * grid.y * (unsigned)warps;  // every warp launched for a plane reports in
-    k_dense_step<COL, T, VEC, PEER><<<grid, block, 0, st>>>(a);
+    // one slot of Q values per thread for the speculatively fetched wall values (only x-face threads use theirs)
+    constexpr size_t keepBytes = VEC > 1 ? (size_t)COL::Q * kStepThreads * sizeof(T) : 0;
+    if constexpr (keepBytes > 48 * 1024) {
+        static bool raised[64] = {};  // per instantiation and device; racing host threads set the same value
+        int         dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+            return cudaErrorInvalidDevice;
+        if (!raised[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k_dense_step<COL, T, VEC, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)keepBytes);
+            if (e != cudaSuccess)
+                return e;
+            raised[dev] = true;
+        }
+    }
+    k_dense_step<COL, T, VEC, PEER><<<grid, block, keepBytes, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -105,6 +105,7 @@ class dGrid:
         d.pop_in = pop_in.data.data_ptr() if pop_in is not None else None
         d.pop_out = pop_out.data.data_ptr() if pop_out is not None else None
         d.flags = flag.words.data_ptr() if flag is not None else None
+        d.wall_cache = pop_out.wallCachePtr() if isinstance(pop_out, dField) else None
         return d
 
     # --- factories (Grid::newField, dGrid.h) ---------------------------------------------------------------------
@@ -150,6 +151,29 @@ class dField(_FieldBase):
         self.data = _aligned_zeros(pop_bytes // self.elem_bytes, _TORCH_DT[dtype], grid.backend.device)
         self.view4 = self.data.view(cardinality, grid.nzm, grid.dim[1], self.pitch_y)
         self._halo_buffers = {}
+        # x-face cache (include/neon_lbm.h, nlbm_dense_wall_cache_build): valid from commitWalls() on; every writer of this
+        # class refreshes it, code that pokes ``data`` directly calls commitWalls() or invalidateWalls() itself
+        self._wall_cache = None
+        self._walls_committed = False
+        if grid.backend.runtime == Runtime.stream:
+            nbytes = C.c_size_t()
+            capi.call("nlbm_dense_wall_cache_layout", C.byref(self._desc), cardinality, self.elem_bytes, C.byref(nbytes))
+            self._wall_cache = torch.zeros(nbytes.value // self.elem_bytes, dtype=_TORCH_DT[dtype], device=grid.backend.device)
+
+    def commitWalls(self, stream_idx: int = 0) -> None:
+        """(Re)builds the x-face cache from the field: call after writing the field other than through the step kernels."""
+        if self._wall_cache is None:
+            return
+        d = self._desc.clone()
+        d.pop_out, d.wall_cache = self.data.data_ptr(), self._wall_cache.data_ptr()
+        capi.call("nlbm_dense_wall_cache_build", C.byref(d), self.cardinality, self.elem_bytes, self.grid.backend.streamHandle(stream_idx))
+        self._walls_committed = True
+
+    def invalidateWalls(self) -> None:
+        self._walls_committed = False
+
+    def wallCachePtr(self):
+        return self._wall_cache.data_ptr() if self._walls_committed else None
 
     # --- host <-> device (FieldBase::updateDeviceData / updateHostData) -------------------------------------------
     def updateDeviceData(self, host, stream_idx: int = 0, host_z0: int = 0) -> None:
@@ -173,6 +197,7 @@ class dField(_FieldBase):
                 self.view4[q, zm0:zm0 + n].copy_(src[q], non_blocking=True)
         else:
             self.view4[:, zm0:zm0 + n, :, :nx].copy_(src, non_blocking=True)
+        self.commitWalls(stream_idx)
 
     def updateHostDataInto(self, host: torch.Tensor) -> None:
         """Asynchronous device -> host copy of the local slab into ``host`` (pinned, [cardinality, nz_local, ny, nx])."""

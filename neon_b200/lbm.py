@@ -62,7 +62,11 @@ class LbmContainers:
         bk = grid.backend
         o = int(arith) | int(opts)
 
+        dense = getattr(grid, "kind", "dense") == "dense"
+
         def launch(streamIdx: int, dataView: DataView) -> None:
+            if dense:  # the output field's x-face cache, if it is current (dField.commitWalls)
+                desc.wall_cache = fOut.wallCachePtr()
             capi.check(fn(C.byref(desc), omega, dataView.value, o, bk.streamHandle(streamIdx)), sym)
 
         c = Container(f"LBM_iteration_D3Q{lattice_q}",

@@ -73,6 +73,8 @@ def init_populations(field: dField, flag: FlagField, q: int, ulb: float = 0.04, 
     d = g.desc(None, field, flag)
     sym = f"nlbm_{g.kind}_init_pop_f32" if field.dtype == np.float32 else f"nlbm_{g.kind}_init_pop_f64"
     capi.call(sym, C.byref(d), q, ulb, g.backend.streamHandle(stream_idx))
+    if hasattr(field, "commitWalls"):
+        field.commitWalls(stream_idx)
 
 
 def setup_device(grid, q: int, dtype, geom: int = CAVITY, sphere=None, ulb: float = 0.04):

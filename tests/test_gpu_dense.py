@@ -335,3 +335,44 @@ def test_large_grid_properties(nb, bk, oracle):
     f = it.getInput().updateHostData().astype(np.float64)
     rho = f.sum(axis=0)[cls == nb.BULK]
     assert abs(rho.mean() - 1.0) < 1e-3 and rho.min() > 0.9 and rho.max() < 1.1
+
+
+@pytest.mark.parametrize("q,store,parts", [(19, np.float32, 1), (27, np.float64, 1), (19, np.float32, 3)])
+def test_x_face_cache_keeps_each_fields_own_wall_values(nb, bk, oracle, q, store, parts):
+    """The x-face cache (nlbm_dense_wall_cache_build) is an optimisation, not a semantic: with it, without it and with wall
+    values that DIFFER between the two fields, non-bulk cells keep exactly what their own field held and bulk cells get
+    the same bits."""
+    from neon_b200 import problems as P
+    results = []
+    for use_cache in (True, False):
+        fields = []
+        for part in range(parts):
+            grid = nb.dGrid(bk, (44, 18, 15), partition=(part, parts))
+            pop0, pop1, flag = P.setup_device(grid, q, store, 1)
+            # make the wall values of pop1 differ from pop0's, x faces included (non-bulk cells only)
+            nonbulk = torch.from_numpy(np.ascontiguousarray(flag.classes() != nb.BULK)).to(bk.device)
+            loc = pop1.view4[:, grid.z_halo:grid.z_halo + grid.nz_local, :, :44]
+            loc[:, nonbulk] = loc[:, nonbulk] * 0.5 + 0.125
+            if use_cache:
+                pop1.commitWalls()
+            else:
+                pop0.invalidateWalls()
+                pop1.invalidateWalls()
+            fields.append((grid, pop0, pop1, flag, pop0.updateHostData().copy(), pop1.updateHostData().copy()))
+        for grid, pop0, pop1, flag, _, _ in fields:
+            assert (pop1.wallCachePtr() is not None) == use_cache
+            a = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop0, pop1, flag, 1.3, q)
+            b = nb.LbmContainers.iteration(nb.StencilSemantic.streaming, pop1, pop0, flag, 1.3, q)
+            a.run(0, nb.DataView.STANDARD)  # ghost planes are not refreshed: the same (stale) data in both runs
+            b.run(0, nb.DataView.STANDARD)
+        bk.syncAll()
+        out = []
+        for grid, pop0, pop1, flag, p0_before, p1_before in fields:
+            nb_mask = np.broadcast_to(flag.classes() != nb.BULK, p0_before.shape)
+            p0, p1 = pop0.updateHostData(), pop1.updateHostData()
+            assert np.array_equal(p0[nb_mask], p0_before[nb_mask]) and np.array_equal(p1[nb_mask], p1_before[nb_mask])
+            assert not np.array_equal(p0[nb_mask], p1[nb_mask])
+            out.append((p0, p1))
+        results.append(out)
+    for (a0, a1), (b0, b1) in zip(*results):
+        assert np.array_equal(a0.view(np.uint8), b0.view(np.uint8)) and np.array_equal(a1.view(np.uint8), b1.view(np.uint8))

@@ -31,6 +31,17 @@
 #define NEON_CUDA_HOST_ONLY
 #endif
 
+/* NVTX ranges as in the reference (compile-time NEON_USE_NVTX, cmake/Nvtx.cmake:3): "Skeleton" around Skeleton::run
+ * (Skeleton.h:59) and one range per container (Graph.cpp:1002,1017).  nvtx3 is header-only. */
+#ifdef NEON_USE_NVTX
+#include <nvtx3/nvToolsExt.h>
+#define NEON_NVTX_PUSH(name) nvtxRangePushA(name)
+#define NEON_NVTX_POP() nvtxRangePop()
+#else
+#define NEON_NVTX_PUSH(name) ((void)0)
+#define NEON_NVTX_POP() ((void)0)
+#endif
+
 namespace Neon {
 
 // ---------------------------------------------------------------------------------------------------- small vectors

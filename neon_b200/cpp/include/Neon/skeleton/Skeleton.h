@@ -12,7 +12,8 @@
 //   Occ::standard  stream 0: INTERNAL            || stream 1: halo update -> BOUNDARY        (fork/join by events)
 // Differences by design: ordering is by CUDA events only (the reference's halo update blocks the host on every device,
 // SynchronizationContainer.h:37-42); the BOUNDARY view is z_local in {0, nz-1} (the reference folds it onto {0,1},
-// SURVEY.md fact 7); with one device a whole run() can be captured once into a CUDA graph and replayed.
+// SURVEY.md fact 7); with one device a whole run() can be captured once into a CUDA graph and replayed (the launches are
+// then frozen: call sequence() again after anything the containers look up at launch time changed, e.g. a field's x-face cache).
 #pragma once
 
 #include <fstream>
@@ -173,7 +174,9 @@ class Skeleton
     {
         const bool graph = mOptions.cudaGraph() && mBk.getDeviceCount() == 1 && mBk.runtime() == Runtime::stream;
         if (!graph) {
+            NEON_NVTX_PUSH("Skeleton");
             issue();
+            NEON_NVTX_POP();
             return;
         }
         mBk.setDevice(0);
@@ -265,7 +268,9 @@ class Skeleton
                     }
                     break;
                 default:
+                    NEON_NVTX_PUSH(n.name.c_str());
                     n.container.run(n.stream, n.view);
+                    NEON_NVTX_POP();
             }
         }
     }

@@ -154,7 +154,7 @@ def cpu_reference(n: int, iters: int, warm: int, fp: str = "float"):
                 if line.startswith("{") and "ref_bench" in line:
                     r = json.loads(line)
                     return {"value": r["mlups"], "unit": "MLUPS", "cores": 1, "kind": "reference", "sample": sample,
-                            "threads_available": os.cpu_count()}
+                            "threads_available": os.cpu_count(), "ms_per_iteration_of_sample": r["elapsed_us"] / max(1, r["timed_iters"]) / 1e3}
         except (OSError, subprocess.SubprocessError, ValueError):
             pass
     import numpy as np
@@ -174,7 +174,7 @@ def cpu_reference(n: int, iters: int, warm: int, fp: str = "float"):
         a, b = b, a
     dt_s = time.perf_counter() - t0
     return {"value": n ** 3 * (iters - warm) / (dt_s * 1e6), "unit": "MLUPS", "cores": 1, "kind": "port", "sample": sample,
-            "threads_available": os.cpu_count()}
+            "threads_available": os.cpu_count(), "ms_per_iteration_of_sample": dt_s * 1e3 / max(1, iters - warm)}
 
 
 def reference_gpu_backend(n: int = 256, iters: int = 60, warm: int = 10):
@@ -209,7 +209,8 @@ def run_reference_arm(args):
     warm = 1
     cb = cpu_reference(n, iters + warm, warm)
     line = {"impl": "reference", "metric": "LBM MLUPS (D3Q19 fp32)", "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": wl["scaling"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb.get("ms_per_iteration_of_sample"), "higher_is_better": True,
+            "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": cb["sample"],
                        "note": "reference = Autodesk/Neon's own LbmIterationD3Q19 on its CPU/OpenMP backend (serial executor), unmodified"},

@@ -163,7 +163,7 @@ int main()
         Backend two({0, 0}, Runtime::openmp);
         auto    active = [](const index_3d& p) { return !(p.x < 8 && p.y < 8 && p.z < 8) && !(p.x >= 16 && p.y == 11 && p.z == 39); };
         bGrid   bg(two, {20, 12, 40}, active, lattice.c_vect);
-        CHECK(bg.getNumPartitions() == 2 && bg.getNumBlocks() == 29);
+        CHECK(bg.getNumPartitions() == 2 && bg.getNumBlocks() == 29 && bg.latticeQ() == 19);
         CHECK(bg.getNumActiveCells() == size_t(20) * 12 * 40 - 512 - 4);
         const auto& p0 = bg.partition(0);  // layers 0..2 (3 of 5), p1: layers 3..4
         const auto& p1 = bg.partition(1);

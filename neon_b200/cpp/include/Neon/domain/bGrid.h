@@ -231,16 +231,8 @@ class bGrid
     const detail::bPartitionInfo& partition(int setIdx) const { return mS->parts.at(setIdx); }
     const uint32_t*               activeMaskDev(int setIdx) const { return mS->parts.at(setIdx).activeMaskDev; }
 
-    int latticeQ() const
-    {
-        dGrid probe; /* same lattice tables */
-        (void)probe;
-        const auto& pts = mS->stencil.points();
-        if (pts.size() == 19) {
-            return 19;
-        }
-        return pts.size() == 27 ? 27 : 0;
-    }
+    /* 19 or 27 if the grid's stencil is one of the two lattices of the kernel library in ITS order, else 0 (same rule as dGrid) */
+    int latticeQ() const { return detail::latticeOf(mS->stencil.points()); }
 
     /* partition descriptor without field pointers */
     nlbm_block_desc descOf(int setIdx) const

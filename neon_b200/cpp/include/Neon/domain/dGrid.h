@@ -130,6 +130,26 @@ inline bool sameOffsets(const std::vector<index_3d>& a, const int (*b)[3], int n
     return true;
 }
 
+/* 19 / 27 when the offsets are D3Q19 (benchmarks/lbm-lid-driven-cavity-flow/src/D3Q19.h:23-44) or D3Q27
+ * (apps/lbmMultiRes/lattice.h:15-77: x slowest, then y, then z, each in the order 0, -1, +1) in the library's order */
+inline int latticeOf(const std::vector<index_3d>& points)
+{
+    static const int d3q19[19][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1},
+                                     {0, -1, -1}, {0, -1, 1}, {0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0},
+                                     {1, -1, 0}, {1, 0, 1}, {1, 0, -1}, {0, 1, 1}, {0, 1, -1}};
+    if (sameOffsets(points, d3q19, 19)) {
+        return 19;
+    }
+    int       d3q27[27][3];
+    const int order[3] = {0, -1, 1};
+    for (int k = 0; k < 27; ++k) {
+        d3q27[k][0] = order[k / 9];
+        d3q27[k][1] = order[(k / 3) % 3];
+        d3q27[k][2] = order[k % 3];
+    }
+    return sameOffsets(points, d3q27, 27) ? 27 : 0;
+}
+
 }  // namespace detail
 
 class dGrid
@@ -190,24 +210,7 @@ class dGrid
     }
 
     /* 19 or 27 if the grid's stencil is one of the two lattices of the kernel library in ITS order, else 0 */
-    int latticeQ() const
-    {
-        static const int d3q19[19][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1},
-                                         {0, -1, -1}, {0, -1, 1}, {0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0},
-                                         {1, -1, 0}, {1, 0, 1}, {1, 0, -1}, {0, 1, 1}, {0, 1, -1}};
-        if (detail::sameOffsets(mS->stencil.points(), d3q19, 19)) {
-            return 19;
-        }
-        /* D3Q27 of apps/lbmMultiRes/lattice.h:15-77: x slowest, then y, then z, each in the order 0, -1, +1 */
-        int       d3q27[27][3];
-        const int order[3] = {0, -1, 1};
-        for (int k = 0; k < 27; ++k) {
-            d3q27[k][0] = order[k / 9];
-            d3q27[k][1] = order[(k / 3) % 3];
-            d3q27[k][2] = order[k % 3];
-        }
-        return detail::sameOffsets(mS->stencil.points(), d3q27, 27) ? 27 : 0;
-    }
+    int latticeQ() const { return detail::latticeOf(mS->stencil.points()); }
 
     /* partition descriptor without pointers */
     nlbm_dense_desc descOf(int setIdx) const

@@ -178,6 +178,18 @@ def test_visual_mode_profiles_match_the_stock_reference_run(app, tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "u_00100.vtk")) and os.path.exists(os.path.join(str(tmp_path), "rho_00000.vtk"))
 
 
+@pytest.mark.gpu
+def test_visual_mode_profiles_fp64_match_the_stock_reference_run(app, tmp_path):
+    """The second set of known answers of the unmodified reference: N=32, fp64/fp64, iteration 100, u_x(y)."""
+    run_app(app, ["--deviceType", "gpu", "--deviceIds", "0", "0", "--domain-size", "32", "--max-iter", "101", "--computeFP", "double",
+                  "--storageFP", "double", "--visual", "--sOCC", "--arith", "reference", "--report-filename", os.path.join(str(tmp_path), "r")],
+            str(tmp_path))
+    y = np.loadtxt(os.path.join(str(tmp_path), "NeonUniformLBM_00100_Y.dat"))
+    for pos, val in {0.25: -0.000756306, 0.5: -0.00128716, 0.75: -0.00239911, 0.9375: 0.0294433}.items():
+        row = y[np.argmin(np.abs(y[:, 0] - pos))]
+        assert abs(row[0] - pos) < 1e-9 and abs(row[1] - val) <= 6e-6 * abs(val), (pos, row[1], val)
+
+
 # ------------------------------------------------------------------------------------------------------------ bGrid
 def _dump_grid(app, tmp_path, grid, *a, **k):
     extra = tuple(k.pop("extra", ())) + ("--grid", grid)

@@ -55,7 +55,8 @@ def parse():
     ap.add_argument("--rows-log2", type=int, default=0)
     ap.add_argument("--flags-summary-first", action="store_true")
     ap.add_argument("--rpw", type=int, default=0, help="rows per warp selector: 0 default, else log2(rows)+1")
-    ap.add_argument("--experiment", type=int, default=0, help="MEASUREMENT ONLY (wrong results): 1 no flags/walls, 2 no edge loads, 3 both")
+    ap.add_argument("--experiment", type=int, default=0, choices=[0, 3],
+                    help="MEASUREMENT ONLY (wrong results): 3 = flags honoured, wall fix-ups and kept wall values skipped")
     ap.add_argument("--no-xface-prefetch", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

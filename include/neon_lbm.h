@@ -88,9 +88,10 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 /* bits 21..23 (direct kernel): rows a warp covers, 0 = library default, else log2(rows) + 1 (1: whole-row warps of 32 lanes,
  * 3: 4 rows x 8 lanes ...).  Narrow warp tiles keep the wall round trip away from most warps.  Never changes results.      */
 #define NLBM_OPT_ROWS_PER_WARP_LOG2P1(r) (((r)&0x7) << 21)
-/* bits 24..26 (direct kernel): MEASUREMENT ONLY — the results are WRONG.  Value 1: every in-box cell is treated as plain
- * bulk and no flag word is loaded (what the streaming part alone reaches); value 2: the flag words are loaded but ignored;
- * value 3: flags are honoured but wall fix-ups and kept wall values are skipped.  Used by bench.py --experiment to attribute the gap to the roofline; never set by the host layers.          */
+/* bits 24..26 (direct kernel): MEASUREMENT ONLY — the results are WRONG.  Value 3: flags are honoured (who is updated) but wall
+ * fix-ups and kept wall values are skipped — what the wall path costs.  (Values 1 "no flag loads, every cell plain bulk" and
+ * 2 "flags loaded but ignored" were used for the attribution of profiles/r01s and are not wired in the shipped kernel.)
+ * Used by bench.py --experiment; never set by the host layers.                                                           */
 #define NLBM_OPT_EXPERIMENT(e) (((e)&0x7) << 24)
 /* bit 27 (direct kernel): do not fetch the output-field values of the cells on the x faces of the box speculatively (default:
  * fetch them with the streaming loads — the kept wall values of those cells are then no dependent DRAM round trip).  Never

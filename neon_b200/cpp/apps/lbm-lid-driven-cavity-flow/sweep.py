@@ -2,8 +2,8 @@
 """Sweep driver for the lid-driven-cavity benchmark binary — the matrix the reference authors intended
 (benchmarks/lbm-lid-driven-cavity-flow/lbm-lid-driven-cavity-flow.py:1-10,52-62: N = 64..512 step 64, grids, store/compute
 precision pairs d/d, f/d, f/f, 1..n GPUs, warm-up 10, 100 iterations, 5 repetitions), with the same report-file naming so
-upstream plotting picks the JSON files up unchanged.  Differences: cpu and eGrid are not on the accelerated path and are
-skipped; --sOCC / transfer mode / halo semantic can be swept too.
+upstream plotting picks the JSON files up unchanged.  Differences: cpu is not on the accelerated path and is skipped; eGrid
+runs on the dense layout (the cavity activates every cell); --sOCC / transfer mode / halo semantic can be swept too.
 
     python sweep.py [--binary PATH] [--sizes 64 128 ...] [--gpus 8] [--grids dGrid bGrid] [--occ nOCC sOCC] [--out DIR] [--dry-run]
 Writes one report JSON per configuration into --out plus sweep.csv (config columns + mean MLUPS).
@@ -42,7 +42,7 @@ def main():
     ap.add_argument("--binary", default=DEFAULT_BINARY)
     ap.add_argument("--sizes", nargs="+", type=int, default=[64, 128, 192, 256, 320, 384, 448, 512])
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--grids", nargs="+", default=["dGrid", "bGrid"])
+    ap.add_argument("--grids", nargs="+", default=["dGrid", "bGrid", "eGrid"])
     ap.add_argument("--occ", nargs="+", default=["nOCC"], choices=["nOCC", "sOCC"])
     ap.add_argument("--transfer", default="get", choices=["get", "put"])
     ap.add_argument("--semantic", default="huLattice", choices=["huLattice", "huGrid"])

@@ -50,6 +50,11 @@ def test_bad_command_line_prints_synopsis(app, tmp_path):
     assert r.returncode != 0 and "unknown option --frobnicate" in r.stdout
 
 
+def test_help_prints_synopsis_and_succeeds(app, tmp_path):
+    r = run_app(app, ["--help"], tmp_path, check=False)
+    assert r.returncode == 0 and "SYNOPSIS" in r.stdout and "--grid <dGrid|bGrid|eGrid>" in r.stdout
+
+
 def test_cpu_device_type_is_refused(app, tmp_path):
     """north star: no CPU fallback — the reference's CPU numbers come from the reference itself"""
     r = run_app(app, ["--deviceType", "cpu", "--deviceIds", "0", "--domain-size", "16", "--max-iter", "2", "--benchmark"], tmp_path,
@@ -79,7 +84,8 @@ def test_sweep_driver_enumerates_the_reference_matrix():
     out = subprocess.run(["python", sweep, "--dry-run", "--gpus", "2"], capture_output=True, text=True, timeout=60).stdout
     assert "'n': 512" in out and "'grid': 'bGrid'" in out and "'devs': '0 1'" in out
     assert "'store': 'double', 'compute': 'float'" not in out
-    assert int(out.strip().splitlines()[-1].split()[0]) == 8 * (3 * 2 + 2 * 2)  # sizes x (dGrid: 3 pairs x 2 device sets + bGrid: 2 x 2)
+    # sizes x (dGrid and eGrid: 3 precision pairs x 2 device sets each + bGrid: 2 pairs x 2)
+    assert int(out.strip().splitlines()[-1].split()[0]) == 8 * (3 * 2 + 3 * 2 + 2 * 2)
 
 
 # ------------------------------------------------------------------------------------------------------------ GPU

@@ -63,6 +63,30 @@ def test_field_layout_and_roundtrip():
     assert not f.view4[..., 20:].any()
 
 
+def test_ranks_upload_their_own_part_of_the_host_mirror():
+    """one process per GPU: a rank holds only the planes it needs (slab + in-box ghost planes) of the host arrays;
+    updateDeviceData / setClasses with host_z0 fill the partition exactly like the global arrays do (bench.py e2e at N > 1)"""
+    bk = nb.Backend(runtime=nb.Runtime.openmp)
+    dim, q = (20, 6, 11), 5
+    rng = np.random.default_rng(1)
+    glob = rng.random((q,) + dim[::-1]).astype(np.float32)
+    cls = rng.integers(0, 3, dim[::-1]).astype(np.int32)
+    for part in range(3):
+        g = nb.dGrid(bk, dim, partition=(part, 3))
+        lo, hi = max(0, g.z_origin - g.z_halo), min(dim[2], g.z_origin + g.nz_local + g.z_halo)
+        a, b = g.newField("a", q, np.float32), g.newField("b", q, np.float32)
+        a.updateDeviceData(glob)
+        b.updateDeviceData(np.ascontiguousarray(glob[:, lo:hi]), host_z0=lo)
+        assert torch.equal(a.data, b.data)
+        fa, fb = g.newFlagField(like=a), g.newFlagField(like=a)
+        fa.setClasses(cls)
+        fb.setClasses(np.ascontiguousarray(cls[lo:hi]), host_z0=lo)
+        assert torch.equal(fa.words, fb.words)
+        assert np.array_equal(fa.classes(), cls[g.z_origin:g.z_origin + g.nz_local])
+        with pytest.raises(AssertionError):
+            b.updateDeviceData(np.ascontiguousarray(glob[:, lo + 1:hi]), host_z0=lo + 1)  # does not cover the partition
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

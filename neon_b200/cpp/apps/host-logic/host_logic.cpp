@@ -47,6 +47,7 @@ int main()
     Backend bk({0, 0, 0}, Runtime::openmp);
     dGrid   grid(bk, {20, 6, 10}, [](const index_3d&) { return true; }, lattice.c_vect);
     CHECK(grid.getNumPartitions() == 3 && grid.zHalo() == 1 && grid.latticeQ() == 19);
+    CHECK(bk.devSet().setCardinality() == 3 && bk.devSet().devId(2) == 0);
     CHECK(grid.nzLocal(0) == 4 && grid.nzLocal(1) == 3 && grid.nzLocal(2) == 3);
     CHECK(grid.zOrigin(0) == 0 && grid.zOrigin(1) == 4 && grid.zOrigin(2) == 7);
     const nlbm_dense_desc d1 = grid.descOf(1);

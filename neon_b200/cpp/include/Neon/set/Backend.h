@@ -81,6 +81,15 @@ class Backend
         setAvailableStreamSet(1);
     }
 
+    /* the slice of Neon::set::DevSet the benchmark-level code asks for (DevSet.h): how many devices, which ids */
+    struct DevSetView
+    {
+        const Backend* bk;
+        int            setCardinality() const { return bk->getDeviceCount(); }
+        int            devId(int setIdx) const { return bk->devId(setIdx); }
+    };
+    DevSetView devSet() const { return DevSetView{this}; }
+
     int     getDeviceCount() const { return int(mS->devIds.size()); }
     int     devId(int setIdx) const { return mS->devIds.at(setIdx); }
     Runtime runtime() const { return mS->runtime; }

@@ -58,6 +58,10 @@ def parse():
     ap.add_argument("--experiment", type=int, default=0, choices=[0, 3],
                     help="MEASUREMENT ONLY (wrong results): 3 = flags honoured, wall fix-ups and kept wall values skipped")
     ap.add_argument("--no-xface-prefetch", action="store_true")
+    ap.add_argument("--opts-extra", type=lambda v: int(v, 0), default=0,
+                    help="OR-ed into the step options (include/neon_lbm.h: 1<<28 flag words with the populations, 1<<29 no "
+                         "speculative x-face fix-up operands); never changes results")
+    ap.add_argument("--no-pipeline", action="store_true", help="N>1: halo update in front of the consumer instead of pushed after BOUNDARY")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="edge of the CPU sample box")
@@ -253,7 +257,7 @@ def main():
     omega = wl.get("omega", nb.omega_from_re(dim[0]))
     arith = nb.ARITH_FAST if args.arith == "fast" else nb.ARITH_REFERENCE
     opts = nb.opt_vec(args.vec) | nb.opt_rows_log2(args.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[args.kernel]) \
-        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0) | ((args.rpw & 7) << 21) | ((args.experiment & 7) << 24) | ((1 << 27) if args.no_xface_prefetch else 0)
+        | capi_opt_tma(args.tma_l2promo, args.tma_groups) | ((1 << 20) if args.flags_summary_first else 0) | ((args.rpw & 7) << 21) | ((args.experiment & 7) << 24) | ((1 << 27) if args.no_xface_prefetch else 0) | args.opts_extra
     occ = nb.Occ.standard if args.occ == "standard" else nb.Occ.none
 
     bk = nb.Backend()
@@ -261,7 +265,7 @@ def main():
     grid = nb.bGrid(bk, dim) if is_block else nb.dGrid(bk, dim)
     pop0, pop1, flag = P.setup_device(grid, q, dtype, wl.get("geom", P.CAVITY), wl.get("sphere"))
     it = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q,
-                         arith=arith, opts=opts, halo_transport=args.transport)
+                         arith=arith, opts=opts, halo_transport=args.transport, pipelined=not args.no_pipeline)
     main_stream = bk.stream(0)
 
     def barrier():
@@ -287,6 +291,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop(t0, t1) if sampler else None
+    if it.timeouts() != 0:  # a face that never arrived: the numbers would come from stale ghost planes
+        raise SystemExit(f"rank {rank}: {it.timeouts()} halo wait(s) timed out — no result")
     ms_step = ms_total / args.steps
     mlups = cells * args.steps / (ms_total * 1e3)
 
@@ -374,6 +380,8 @@ def main():
         it2.getInput().updateHostDataInto(out_h)
         barrier()
         w1 = time.perf_counter()
+        if it2.timeouts() != 0:
+            raise SystemExit(f"rank {rank}: {it2.timeouts()} halo wait(s) timed out in the end-to-end run — no result")
         secs = torch.tensor([w1 - w0], dtype=torch.float64, device=bk.device)
         traffic_hd = torch.tensor([2.0 * pop_h.numel() * dtype.itemsize + cls.size * 4, float(out_h.numel() * dtype.itemsize)],
                                   dtype=torch.float64, device=bk.device)

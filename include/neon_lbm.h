@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define NLBM_ABI_VERSION 2
+#define NLBM_ABI_VERSION 3
 
 typedef enum nlbm_status {
     NLBM_OK = 0,
@@ -97,6 +97,14 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * fetch them with the streaming loads — the kept wall values of those cells are then no dependent DRAM round trip).  Never
  * changes results.                                                                                                      */
 #define NLBM_OPT_NO_XFACE_PREFETCH (1 << 27)
+/* bit 28 (direct kernel): fetch the 4-byte flag word of EVERY cell together with the populations (the round-1 default).
+ * Default (bit clear): each thread reads one byte of the cell map (1 byte per 4 cells, kept behind the flag words by the
+ * set-up calls) with its populations and fetches flag words only where a bulk cell has wall bits or shares the thread with a
+ * non-bulk cell — 0.25 instead of 4 B/cell of flag traffic.  Never changes results.                                      */
+#define NLBM_OPT_FLAG_WORDS (1 << 28)
+/* bit 29 (direct kernel): do not fetch the wall fix-up operands of the cells next to the x faces speculatively (default: they
+ * travel with the streaming loads, and are used only if the cell's wall bits are exactly the x-face set).  Never changes results. */
+#define NLBM_OPT_NO_XFACE_FIXUP_PREFETCH (1 << 29)
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2
@@ -112,8 +120,9 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  *   request of 32 x 16 bytes); base pointers 128-byte aligned.
  * The flag array uses the same (zm,y,x) indexing with pitch_y / pitch_z.  Behind the
  * per-cell words the SAME buffer holds a small per-row summary (which 32-cell chunks
- * contain anything but plain bulk cells) that lets the step kernels skip flag loads;
- * nlbm_dense_classify / nlbm_dense_wall_mask keep it current, and a caller that writes
+ * contain anything but plain bulk cells) and a cell map (one byte per 4 cells: which are
+ * bulk, which are anything but plain bulk) that let the step kernels skip flag loads;
+ * nlbm_dense_classify / nlbm_dense_wall_mask keep both current, and a caller that writes
  * flag words itself must call nlbm_dense_flags_commit before stepping.
  * (Reference: unpadded SoA, dField_imp.h:67-87.)                                 */
 typedef struct nlbm_dense_desc {
@@ -159,7 +168,7 @@ int nlbm_dense_wall_cache_build(const nlbm_dense_desc* d, int q, int elem_bytes,
  * in global cells or NULL for the default (0.45nx, 0.55ny, 0.5nz, min(n)/5).
  * Writes the class bits of every plane including ghosts (mask bits cleared).       */
 int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream);
-/* Rebuilds the per-row summary from the flag words (after the caller wrote them itself). */
+/* Rebuilds the per-row summary and the cell map from the flag words (after the caller wrote them itself). */
 int nlbm_dense_flags_commit(const nlbm_dense_desc* d, void* stream);
 /* LbmContainers::computeWallNghMask, LbmTools.h:344-376 (bit-exact).  q = 19|27.
  * Needs valid class bits in the ghost planes.  *d_bad (device int32, may be NULL) is
@@ -221,6 +230,15 @@ int nlbm_d3q19_f64_dense_rho_u(const nlbm_dense_desc* d, void* rho, void* u, voi
  * kernel then stores straight into the peer's HBM over NVLink.                       */
 int nlbm_dense_halo_push(const nlbm_dense_desc* src_desc, const void* src_field, const nlbm_dense_desc* dst_desc,
                          void* dst_field, int elem_bytes, int ncomp, int lattice_q, int dir, void* stream);
+/* Both faces of a partition in ONE launch, signalling included (replaces the same 2 x 19 cudaMemcpyPeerAsync + host syncs,
+ * DataTransferContainer.h:38-55 / SynchronizationContainer.h:37-42): src's top plane goes into the lower ghost plane of the
+ * neighbour above (up_field: its field through a peer / CUDA-IPC mapping, up_nz_local: its slab height), src's bottom plane
+ * into the upper ghost plane of the neighbour below; when all stores of the launch are out, `value` is published in both
+ * neighbours' flag words (nlbm_flag_wait2 on their side).  Either neighbour may be NULL.  counter: one word of device
+ * memory on THIS GPU, zero before the first call, owned by the caller.                                                  */
+int nlbm_dense_halo_push2(const nlbm_dense_desc* src_desc, const void* src_field, void* up_field, int32_t up_nz_local, uint32_t* up_flag,
+                          void* down_field, int32_t down_nz_local, uint32_t* down_flag, uint32_t* counter, uint32_t value,
+                          int elem_bytes, int ncomp, int lattice_q, void* stream);
 /* Staged variant for transports that cannot map peer memory (NCCL send/recv):
  * pack the crossing populations of one boundary plane into a contiguous buffer and
  * unpack such a buffer into a ghost plane.  Returns the byte count in *bytes.        */
@@ -285,8 +303,12 @@ int nlbm_block_halo_push(const nlbm_block_desc* src_desc, const void* src_field,
  * across processes a counter word in the receiver's memory replaces the event.
  *   nlbm_flag_signal: enqueue "*flag = value" after everything already in `stream` (system-wide visibility);
  *                     `flag` may be a CUDA-IPC / peer mapping of memory on the neighbouring GPU.
- *   nlbm_flag_wait  : enqueue a wait until *flag >= value (wrap-safe) or until timeout_ms elapsed, in which case
- *                     *d_err (device int32, may be NULL) is incremented and the stream continues.                   */
+ *   nlbm_flag_wait  : enqueue a wait until *flag >= value (wrap-safe).  If timeout_ms elapse first, *d_err (device int32,
+ *                     may be NULL) is incremented and the kernel TRAPS: the work queued behind the wait would read a ghost
+ *                     plane that never arrived, so the failure is made fatal for the process (every later CUDA call
+ *                     returns an error) instead of letting the stream continue on stale data.
+ *   nlbm_flag_wait2 : the same for two flag words in one launch (a partition has at most two z-neighbours); either may
+ *                     be NULL.                                                                                      */
 /* CUDA-IPC plumbing for the peer-store transport between processes.  export: handle of the ALLOCATION that contains `ptr`
  * and ptr's byte offset inside it; import (in another process, with ITS device current): maps that allocation and returns
  * its base — peer access to the exporting device is enabled on demand.  A handle must be imported once per process.       */
@@ -298,6 +320,7 @@ int nlbm_ipc_close(void* base);
 int nlbm_enable_peer_access(int peer_device);
 int nlbm_flag_signal(uint32_t* flag, uint32_t value, void* stream);
 int nlbm_flag_wait(const uint32_t* flag, uint32_t value, uint32_t timeout_ms, int32_t* d_err, void* stream);
+int nlbm_flag_wait2(const uint32_t* flag_a, const uint32_t* flag_b, uint32_t value, uint32_t timeout_ms, int32_t* d_err, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,8 +4,8 @@ Only what the path needs: the C-ABI kernel library (csrc/ -> lib/libneon_lbm.so,
 mirror of the reference interface for it (Backend, dGrid/dField, Container, Skeleton with OCC, LbmIteration).
 """
 from ._capi import (ARITH_FAST, ARITH_REFERENCE, BOUNCE_BACK, BULK, KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, MOVING_WALL, UNDEFINED,
-                    NeonException, opt_kernel, opt_rows_log2,
-                    opt_vec)
+                    NeonException, OPT_FLAG_WORDS, OPT_FLAGS_SUMMARY_FIRST, OPT_NO_XFACE_FIXUP_PREFETCH, OPT_NO_XFACE_PREFETCH,
+                    opt_kernel, opt_rows_log2, opt_vec)
 from .backend import Backend, Runtime
 from .bgrid import bField, bFlagField, bGrid
 from .containers import Access, Container, Pattern, Token

@@ -39,6 +39,13 @@ def opt_tma(l2promo: int = 0, groups: int = 0) -> int:
     return ((l2promo & 3) << 16) | ((groups & 3) << 18)
 
 
+# direct-kernel variants (never change results; include/neon_lbm.h bits 20, 27, 28, 29)
+OPT_FLAGS_SUMMARY_FIRST = 1 << 20
+OPT_NO_XFACE_PREFETCH = 1 << 27
+OPT_FLAG_WORDS = 1 << 28
+OPT_NO_XFACE_FIXUP_PREFETCH = 1 << 29
+
+
 class NeonException(RuntimeError):
     """Counterpart of Neon::NeonException (libNeonCore/include/Neon/core/types/Exceptions.h:19-24): every non-zero
     status of the C layer is converted into this, as the reference does for every failed CUDA call."""
@@ -127,6 +134,8 @@ _SIGNATURES = {
     "nlbm_enable_peer_access": (C.c_int, [C.c_int]),
     "nlbm_flag_signal": (C.c_int, [_P, C.c_uint32, _P]),
     "nlbm_flag_wait": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
+    "nlbm_flag_wait2": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P]),
+    "nlbm_dense_halo_push2": (C.c_int, [_D, _P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_uint32, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 _lib = None

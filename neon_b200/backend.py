@@ -56,8 +56,10 @@ class Backend:
             if self.runtime == Runtime.stream:
                 # stream 0 is the main stream (made torch's current stream so that tensor copies are ordered with
                 # the kernels; an explicit stream, so a whole Skeleton run can be captured into a CUDA graph); the
-                # others are side streams for halo + boundary work
-                self._streams.append(torch.cuda.Stream(self.device))
+                # others are side streams for halo + boundary work, created with HIGH priority: a small BOUNDARY kernel or
+                # face copy must not queue behind the thousands of blocks of the INTERNAL kernel on the main stream
+                # (round 1: the side stream's work ran in INTERNAL's tail, 104 us per iteration, profiles/r01l)
+                self._streams.append(torch.cuda.Stream(self.device, priority=0 if not self._streams else -1))
                 if len(self._streams) == 1:
                     torch.cuda.set_stream(self._streams[0])
             else:

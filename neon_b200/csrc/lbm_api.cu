@@ -152,12 +152,15 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     a.pitch_q = d->pitch_q;
     a.wpr = (int32_t)nlbm::summaryWordsPerRow(d->pitch_y);
     a.omega = omega;
-    a.flagsAlways = ((opts >> 20) & 1) ? 0 : 1;
+    // how a thread learns about its cells: default the cell map; NLBM_OPT_FLAG_WORDS / NLBM_OPT_FLAGS_SUMMARY_FIRST select the others
+    a.flagMode = ((opts >> 28) & 1) ? nlbm::kFlagWords : (((opts >> 20) & 1) ? nlbm::kFlagSummaryFirst : nlbm::kFlagCellMap);
+    a.cellMap = nlbm::cellMapPtr(*d);
     a.prefetchXFaces = ((opts >> 27) & 1) ? 0 : 1;  // NLBM_OPT_NO_XFACE_PREFETCH
+    a.specXFix = ((opts >> 29) & 1) ? 0 : 1;        // NLBM_OPT_NO_XFACE_FIXUP_PREFETCH
     a.keepCache = d->wall_cache;
     a.experiment = (opts >> 24) & 0x7;  // NLBM_OPT_EXPERIMENT: measurement only
     if (a.experiment)
-        a.flagsAlways = 1;
+        a.flagMode = nlbm::kFlagWords;
     a.lprLog2 = 5;
     a.peerMode = 0;
     a.nzLocal = d->nz_local;
@@ -309,8 +312,7 @@ int nlbm_dense_layout(nlbm_dense_desc* d, int q, int elem_bytes, size_t* pop_byt
     if (pop_bytes)
         *pop_bytes = (size_t)q * (size_t)d->pitch_q * (size_t)elem_bytes;
     if (flag_bytes) {
-        const int64_t rows = (int64_t)d->ny * (d->nz_local + 2 * d->z_halo);
-        *flag_bytes = (size_t)(nlbm::flagCellWords(*d) + 2 * rows * nlbm::summaryWordsPerRow(d->pitch_y)) * 4;
+        *flag_bytes = (size_t)nlbm::flagBufferBytes(*d);  // flag words + row summary + cell map
     }
     return NLBM_OK;
 }
@@ -455,6 +457,49 @@ int nlbm_dense_halo_push(const nlbm_dense_desc* s, const void* src_field, const 
     }
     cudaError_t e = nlbm::launchPlaneCopy(src_field, dst_field, pl, (size_t)s->pitch_z * elem_bytes, (cudaStream_t)stream);
     return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo push launch");
+}
+
+int nlbm_dense_halo_push2(const nlbm_dense_desc* s, const void* src_field, void* up_field, int32_t up_nz_local, uint32_t* up_flag,
+                          void* down_field, int32_t down_nz_local, uint32_t* down_flag, uint32_t* counter, uint32_t value,
+                          int elem_bytes, int ncomp, int lattice_q, void* stream)
+{
+    if (int rc = checkHalo(s, elem_bytes, ncomp, lattice_q, 1))
+        return rc;
+    if (!src_field)
+        return fail(NLBM_ERR_INVALID, "null field");
+    if (s->z_halo < 1)
+        return fail(NLBM_ERR_INVALID, "the partition has no z-neighbours (z_halo = 0)");
+    if (!counter || ((uintptr_t)counter & 3))
+        return fail(NLBM_ERR_INVALID, "counter null or misaligned");
+    if ((up_field && (!up_flag || up_nz_local < 1)) || (down_field && (!down_flag || down_nz_local < 1)))
+        return fail(NLBM_ERR_INVALID, "a neighbour needs its field, flag word and slab height");
+    if (((uintptr_t)up_flag | (uintptr_t)down_flag) & 3)
+        return fail(NLBM_ERR_INVALID, "flag pointer misaligned");
+    int             list[27];
+    nlbm::PlaneList pl;
+    pl.n = 0;
+    int nUp = 0;
+    if (up_field) {  // my top plane -> the lower ghost plane (memory plane 0) of the neighbour above
+        const int     n = crossing(lattice_q, ncomp, +1, list);
+        const int64_t zs = s->z_halo + s->nz_local - 1, pq = s->pitch_z * (up_nz_local + 2);
+        for (int i = 0; i < n; ++i, ++pl.n) {
+            pl.src[pl.n] = (list[i] * s->pitch_q + zs * s->pitch_z) * elem_bytes;
+            pl.dst[pl.n] = (list[i] * pq) * elem_bytes;
+        }
+        nUp = n;
+    }
+    if (down_field) {  // my bottom plane -> the upper ghost plane (memory plane nz + 1) of the neighbour below
+        const int     n = crossing(lattice_q, ncomp, -1, list);
+        const int64_t zs = s->z_halo, pq = s->pitch_z * (down_nz_local + 2), zd = down_nz_local + 1;
+        for (int i = 0; i < n; ++i, ++pl.n) {
+            pl.src[pl.n] = (list[i] * s->pitch_q + zs * s->pitch_z) * elem_bytes;
+            pl.dst[pl.n] = (list[i] * pq + zd * s->pitch_z) * elem_bytes;
+        }
+    }
+    cudaError_t e = nlbm::launchFacePush2(src_field, pl, nUp, up_field, down_field, up_field ? up_flag : nullptr,
+                                          down_field ? down_flag : nullptr, counter, value, (size_t)s->pitch_z * elem_bytes,
+                                          (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "halo push2 launch");
 }
 
 int nlbm_dense_halo_pack(const nlbm_dense_desc* d, const void* field, int elem_bytes, int ncomp, int lattice_q, int dir,
@@ -726,7 +771,17 @@ int nlbm_flag_wait(const uint32_t* flag, uint32_t value, uint32_t timeout_ms, in
         return fail(NLBM_ERR_INVALID, "flag pointer null or misaligned");
     if (timeout_ms == 0)
         return fail(NLBM_ERR_INVALID, "a wait needs a time-out");
-    cudaError_t e = nlbm::launchFlagWait(flag, value, timeout_ms, d_err, (cudaStream_t)stream);
+    cudaError_t e = nlbm::launchFlagWait(flag, nullptr, value, timeout_ms, d_err, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag wait launch");
+}
+
+int nlbm_flag_wait2(const uint32_t* flag_a, const uint32_t* flag_b, uint32_t value, uint32_t timeout_ms, int32_t* d_err, void* stream)
+{
+    if ((!flag_a && !flag_b) || (((uintptr_t)flag_a | (uintptr_t)flag_b) & 3))
+        return fail(NLBM_ERR_INVALID, "flag pointers null or misaligned");
+    if (timeout_ms == 0)
+        return fail(NLBM_ERR_INVALID, "a wait needs a time-out");
+    cudaError_t e = nlbm::launchFlagWait(flag_a, flag_b, value, timeout_ms, d_err, (cudaStream_t)stream);
     return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag wait launch");
 }
 

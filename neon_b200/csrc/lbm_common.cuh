@@ -83,6 +83,23 @@ inline __host__ __device__ const uint2* summaryPtr(const nlbm_dense_desc& d)
 {
     return reinterpret_cast<const uint2*>(d.flags + flagCellWords(d));
 }
+// Cell map, behind the row summary in the same buffer: ONE BYTE per 4 consecutive cells of a row (pitch_y / 4 bytes per
+// row, rows as in the flag array):  bit i (0..3) set <=> cell 4g+i is bulk;  bit 4+i set <=> cell 4g+i is not "plain bulk"
+// (non-bulk, wall bits set, or x >= nx).  A thread of the step kernel reads its byte together with the populations and
+// needs the 4-byte flag words only where a bulk cell has wall bits or sits next to a non-bulk cell in the same thread:
+// 0.25 B/cell of traffic instead of 4 B/cell, and no dependent round trip for plain threads.
+__host__ __device__ inline int64_t cellMapBytesPerRow(int64_t pitch_y) { return pitch_y / 4; }
+__host__ __device__ inline int64_t flagRows(const nlbm_dense_desc& d) { return (int64_t)d.ny * (d.nz_local + 2 * d.z_halo); }
+inline __host__ __device__ const uint8_t* cellMapPtr(const nlbm_dense_desc& d)
+{
+    return reinterpret_cast<const uint8_t*>(summaryPtr(d) + flagRows(d) * summaryWordsPerRow(d.pitch_y));
+}
+__host__ __device__ inline int64_t flagBufferBytes(const nlbm_dense_desc& d)
+{
+    return (flagCellWords(d) + 2 * flagRows(d) * summaryWordsPerRow(d.pitch_y)) * 4 + alignUp(flagRows(d) * cellMapBytesPerRow(d.pitch_y), 128);
+}
+
+enum FlagMode { kFlagWords = 0, kFlagSummaryFirst = 1, kFlagCellMap = 2 };
 
 // ---------------------------------------------------------------- kernel arguments (by value)
 struct DenseArgs
@@ -98,7 +115,11 @@ struct DenseArgs
     int32_t zm0;          // first memory plane of the view
     int32_t fold, skip;   // view planes >= fold are shifted by skip (BOUNDARY view: two slabs)
     int32_t lprLog2;      // direct kernel: log2 of the lanes a warp spends on one row (32 = whole-row warps)
-    int32_t flagsAlways;  // direct kernel: fetch the flag words with the populations instead of consulting the row summary first
+    int32_t flagMode;     // direct kernel: how a thread learns about its cells — kFlagWords: the flag words travel with the
+                          // populations; kFlagSummaryFirst: row summary first, flag words only for non-plain chunks;
+                          // kFlagCellMap: one byte per 4 cells with the populations, flag words only for non-plain threads
+    const uint8_t* cellMap;
+    int32_t specXFix;     // direct kernel: fetch the wall fix-up operands of the cells next to the x faces speculatively (cp.async)
     int32_t prefetchXFaces;  // direct kernel: fetch the output-field values of the cells at x = 0 and x = nx-1 speculatively (cp.async)
     const void* keepCache;   // x-face cache of the output field (nlbm_dense_wall_cache_build) or null
     int32_t experiment;   // MEASUREMENT ONLY (results are wrong): 1 every cell is plain bulk, no flag loads; 2 flags loaded but ignored
@@ -245,6 +266,13 @@ __device__ __forceinline__ void ldFlags(const uint32_t* p, bool pred, uint32_t (
                      : "l"(p), "r"((uint32_t)pred));
     else
         asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.u32 %0, [%1];\n}\n" : "+r"(v[0]) : "l"(p), "r"((uint32_t)pred));
+}
+// one byte of the cell map; pred == false yields 0 (no bulk cell)
+__device__ __forceinline__ uint32_t ldPredU8(const uint8_t* p, bool pred)
+{
+    uint32_t v = 0;
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.u8 %0, [%1];\n}\n" : "+r"(v) : "l"(p), "r"((uint32_t)pred));
+    return v;
 }
 __device__ __forceinline__ uint2 ldPredU2(const uint2* p)
 {

@@ -37,6 +37,67 @@ cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, siz
     return cudaGetLastError();
 }
 
+// Both faces of a partition in ONE launch, signalling included: planes [0, nUp) go to the neighbour above, the rest to the
+// neighbour below; the last block to finish publishes `value` in both neighbours' flag words (what k_flag_signal would do
+// in two more launches).  counter: one word of local memory, zero between launches.
+struct Push2Args
+{
+    PlaneList pl;
+    int       nUp;
+    char*     dst[2];       // [0] neighbour above, [1] neighbour below (peer mappings)
+    uint32_t* flag[2];      // their flag words (peer mappings), null where there is no neighbour
+    uint32_t* counter;
+    uint32_t  value, blocks;
+};
+__global__ void __launch_bounds__(256) k_face_push2(const char* __restrict__ src, const Push2Args a, const size_t vecPerPlane)
+{
+    const int    p = blockIdx.y;
+    const uint4* s = reinterpret_cast<const uint4*>(src + a.pl.src[p]);
+    uint4*       d = reinterpret_cast<uint4*>(a.dst[p < a.nUp ? 0 : 1] + a.pl.dst[p]);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecPerPlane; i += stride)
+        d[i] = __ldcs(s + i);
+    __threadfence_system();  // my peer stores are visible system-wide before my block counts as done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(a.counter, 1u);
+        if (done == a.blocks - 1) {
+            *a.counter = 0;  // ready for the next launch
+            __threadfence_system();
+            for (int k = 0; k < 2; ++k)
+                if (a.flag[k])
+                    *reinterpret_cast<volatile uint32_t*>(a.flag[k]) = a.value;
+            __threadfence_system();
+        }
+    }
+}
+
+cudaError_t launchFacePush2(const void* src, const PlaneList& pl, int nUp, void* dstUp, void* dstDown, uint32_t* flagUp,
+                            uint32_t* flagDown, uint32_t* counter, uint32_t value, size_t planeBytes, cudaStream_t st)
+{
+    if (pl.n == 0 || planeBytes == 0)
+        return cudaSuccess;
+    const size_t vecs = planeBytes / 16;
+    size_t       bx = (vecs + 256 * 4 - 1) / (256 * 4);
+    if (bx > 148 * 2)
+        bx = 148 * 2;
+    if (bx == 0)
+        bx = 1;
+    Push2Args a;
+    a.pl = pl;
+    a.nUp = nUp;
+    a.dst[0] = (char*)dstUp;
+    a.dst[1] = (char*)dstDown;
+    a.flag[0] = flagUp;
+    a.flag[1] = flagDown;
+    a.counter = counter;
+    a.value = value;
+    a.blocks = (uint32_t)(bx * pl.n);
+    dim3 grid((unsigned)bx, pl.n);
+    k_face_push2<<<grid, 256, 0, st>>>((const char*)src, a, vecs);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- block-sparse faces
 // One z-slice (64 cells = 256 / 512 contiguous bytes) of every boundary block and crossing population.
 struct SliceArgs
@@ -91,7 +152,9 @@ cudaError_t launchBlockSliceCopy(const void* src, void* dst, int elemBytes, cons
 // One process per GPU cannot order a neighbour's stream with CUDA events without a host hand-shake per iteration.  The
 // peer-store halo transport therefore orders with flag words: after its face copy (stream order) the sender publishes a
 // counter in the receiver's memory, and the receiver's stream holds a one-thread kernel that waits for it.  The wait
-// gives up after timeoutMs (and records it) so that a lost neighbour cannot hang the GPU.
+// gives up after timeoutMs so that a lost neighbour cannot hang the GPU — and then it TRAPS: the step kernel behind it
+// would read a stale or half-written ghost plane, so the error must not be survivable.  *err is incremented first (for a
+// host that still can read it); after the trap every later CUDA call of the process fails.
 __global__ void k_flag_signal(volatile uint32_t* flag, uint32_t value)
 {
     __threadfence_system();  // the face copy of the previous kernel in this stream is visible system-wide first
@@ -99,18 +162,27 @@ __global__ void k_flag_signal(volatile uint32_t* flag, uint32_t value)
     __threadfence_system();
 }
 
-__global__ void k_flag_wait(const volatile uint32_t* flag, uint32_t value, unsigned long long timeoutNs, int32_t* err)
+// waits for up to two flag words (a partition has at most two z-neighbours); a null pointer is not waited for
+__global__ void k_flag_wait(const volatile uint32_t* flag0, const volatile uint32_t* flag1, uint32_t value, unsigned long long timeoutNs,
+                            int32_t* err)
 {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while ((int32_t)(*flag - value) < 0) {  // counters only grow; the signed difference tolerates wrap-around
-        __nanosleep(200);
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > timeoutNs) {
-            if (err)
-                atomicAdd(err, 1);
-            break;
+    const volatile uint32_t* flags[2] = {flag0, flag1};
+    for (int k = 0; k < 2; ++k) {
+        if (!flags[k])
+            continue;
+        while ((int32_t)(*flags[k] - value) < 0) {  // counters only grow; the signed difference tolerates wrap-around
+            __nanosleep(200);
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeoutNs) {
+                if (err) {
+                    atomicAdd(err, 1);
+                    __threadfence_system();
+                }
+                __trap();  // fatal: whatever follows in this stream would compute on a ghost plane that never arrived
+            }
         }
     }
     __threadfence_system();
@@ -121,9 +193,9 @@ cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t st)
     k_flag_signal<<<1, 1, 0, st>>>(flag, value);
     return cudaGetLastError();
 }
-cudaError_t launchFlagWait(const uint32_t* flag, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st)
+cudaError_t launchFlagWait(const uint32_t* flag0, const uint32_t* flag1, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st)
 {
-    k_flag_wait<<<1, 1, 0, st>>>(flag, value, (unsigned long long)timeoutMs * 1000000ull, err);
+    k_flag_wait<<<1, 1, 0, st>>>(flag0, flag1, value, (unsigned long long)timeoutMs * 1000000ull, err);
     return cudaGetLastError();
 }
 

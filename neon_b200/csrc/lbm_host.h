@@ -53,11 +53,13 @@ cudaError_t launchBlockSliceCopy(const void* src, void* dst, int elemBytes, cons
 struct PlaneList
 {
     int     n;
-    int64_t src[27];  // byte offsets
-    int64_t dst[27];
+    int64_t src[54];  // byte offsets (up to 2 x 27: both faces of a partition in one launch)
+    int64_t dst[54];
 };
 cudaError_t launchFlagSignal(uint32_t* flag, uint32_t value, cudaStream_t st);
-cudaError_t launchFlagWait(const uint32_t* flag, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st);
+cudaError_t launchFlagWait(const uint32_t* flag0, const uint32_t* flag1, uint32_t value, uint32_t timeoutMs, int32_t* err, cudaStream_t st);
+cudaError_t launchFacePush2(const void* src, const PlaneList& pl, int nUp, void* dstUp, void* dstDown, uint32_t* flagUp, uint32_t* flagDown,
+                            uint32_t* counter, uint32_t value, size_t planeBytes, cudaStream_t st);
 cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, size_t planeBytes, cudaStream_t st);
 
 }  // namespace nlbm

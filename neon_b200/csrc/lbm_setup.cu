@@ -93,9 +93,9 @@ __global__ void k_wall_mask(const GeomArgs g, int32_t* __restrict__ bad)
         atomicAdd(bad, nbad);
 }
 
-// one warp per (row, summary word): 32 chunks of 32 cells
-__global__ void k_summary(const uint32_t* __restrict__ flags, uint2* __restrict__ summary, int nx, int ny, int nzm,
-                          int pitch_y, int64_t pitch_z, int wpr)
+// one warp per (row, summary word): 32 chunks of 32 cells; also writes the cell map (one byte per 4 cells, lbm_common.cuh)
+__global__ void k_summary(const uint32_t* __restrict__ flags, uint2* __restrict__ summary, uint8_t* __restrict__ cellMap, int nx, int ny,
+                          int nzm, int pitch_y, int64_t pitch_z, int wpr)
 {
     const int     lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -115,10 +115,14 @@ __global__ void k_summary(const uint32_t* __restrict__ flags, uint2* __restrict_
             isBulk = flagIsBulk(f);
             isSpec = f != kPlainBulk;
         }
-        if (__any_sync(0xffffffffu, isSpec))
+        const uint32_t ms = __ballot_sync(0xffffffffu, isSpec), mb = __ballot_sync(0xffffffffu, isBulk);
+        if (ms)
             spec |= 1u << c;
-        if (__any_sync(0xffffffffu, isBulk))
+        if (mb)
             bulk |= 1u << c;
+        const int xg = (word * 32 + c) * kChunk;  // first cell of the chunk: lanes 0..7 write the bytes of its 8 groups of 4 cells
+        if (lane < 8 && xg + 4 * lane < pitch_y)
+            cellMap[row * (pitch_y >> 2) + (xg >> 2) + lane] = (uint8_t)(((mb >> (4 * lane)) & 0xFu) | (((ms >> (4 * lane)) & 0xFu) << 4));
     }
     if (lane == 0)
         summary[row * wpr + word] = make_uint2(spec, bulk);
@@ -276,8 +280,8 @@ cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st)
     const int64_t warps = (int64_t)d.ny * nzm * wpr;
     const int     threads = 256;
     const int64_t blocks = (warps * 32 + threads - 1) / threads;
-    k_summary<<<(unsigned)blocks, threads, 0, st>>>(d.flags, const_cast<uint2*>(summaryPtr(d)), d.nx, d.ny, nzm,
-                                                    (int)d.pitch_y, d.pitch_z, wpr);
+    k_summary<<<(unsigned)blocks, threads, 0, st>>>(d.flags, const_cast<uint2*>(summaryPtr(d)), const_cast<uint8_t*>(cellMapPtr(d)), d.nx,
+                                                    d.ny, nzm, (int)d.pitch_y, d.pitch_z, wpr);
     return cudaGetLastError();
 }
 

@@ -346,12 +346,73 @@ __device__ __forceinline__ void fixCell(const T* __restrict__ cell, const DenseA
     static_assert(NP <= 3 * CH, "chunking covers three batches");
 }
 
+// Populations whose pull source lies across an x face of the box.  A bulk cell at x = 1 whose only non-bulk neighbours
+// are the three (D3Q19: five directions, D3Q27: nine) in the plane x = 0 carries exactly the bits of the populations
+// with c_x = +1 (side 0); at x = nx-2 those with c_x = -1 (side 1), the opposites of the first set.  The step kernel
+// fetches the operands of that fix-up speculatively with its streaming loads; the flag word decides whether they are used.
+template <class L>
+struct XSet
+{
+    __host__ __device__ static constexpr int count()
+    {
+        int n = 0;
+        for (int q = 0; q < L::Q; ++q)
+            n += L::c(q, 0) == 1;
+        return n;
+    }
+    static constexpr int N = count();
+    // k-th population with c_x = +1
+    __host__ __device__ static constexpr int q(int k)
+    {
+        int n = 0;
+        for (int i = 0; i < L::Q; ++i) {
+            if (L::c(i, 0) == 1) {
+                if (n == k)
+                    return i;
+                ++n;
+            }
+        }
+        return -1;
+    }
+    __host__ __device__ static constexpr uint32_t mask(int side)
+    {
+        uint32_t m = 0;
+        for (int i = 0; i < L::Q; ++i)
+            if (L::c(i, 0) == (side ? -1 : 1))
+                m |= 1u << i;
+        return m;
+    }
+};
+
+template <class L, typename T, int VEC, int... Ks>
+__device__ __forceinline__ void xFixIssue(std::integer_sequence<int, Ks...>, T* sSlot, const T* __restrict__ cell, const DenseArgs& a,
+                                          const int side)
+{
+    // side 0: in[q] = f_o(x) + f_o(x - c_q), q with c_x = +1, o = opp(q);  side 1: the roles of q and o swap
+    constexpr int N = XSet<L>::N;
+    const int     sgn = side ? -1 : 1;
+    ((cpAsync1(sSlot + (L::Q + Ks) * kStepThreads, cell + (int64_t)(side ? XSet<L>::q(Ks) : L::opp(XSet<L>::q(Ks))) * a.pitch_q),
+      cpAsync1(sSlot + (L::Q + N + Ks) * kStepThreads,
+               cell + (int64_t)(side ? XSet<L>::q(Ks) : L::opp(XSet<L>::q(Ks))) * a.pitch_q -
+                   sgn * (L::c(XSet<L>::q(Ks), 2) * a.pitch_z + (int64_t)L::c(XSet<L>::q(Ks), 1) * a.pitch_y + 1))),
+     ...);
+}
+template <class L, typename T, int VEC, int... Ks>
+__device__ __forceinline__ void xFixUse(std::integer_sequence<int, Ks...>, const T* sSlot, const int side, const int i, T (&f)[L::Q][VEC])
+{
+    constexpr int N = XSet<L>::N;
+    // the sum lands in slot q (side 0) or opp(q) (side 1)
+    ((side ? (void)(f[L::opp(XSet<L>::q(Ks))][i] = sSlot[(L::Q + Ks) * kStepThreads] + sSlot[(L::Q + N + Ks) * kStepThreads])
+           : (void)(f[XSet<L>::q(Ks)][i] = sSlot[(L::Q + Ks) * kStepThreads] + sSlot[(L::Q + N + Ks) * kStepThreads])),
+     ...);
+}
+
 // Wall fix-ups, collision and stores of the VEC cells one thread owns (shared by the direct and the TMA kernel).
 template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5)>
 __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
                                             const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC],
                                             T* __restrict__ peerDst = nullptr, const int64_t peerPitchQ = 0, const int peerDir = 0,
-                                            const T* sKeep = nullptr, const int specCell = -1)
+                                            const T* sKeep = nullptr, const int specCell = -1, const int specAdj = -1, const int specSide = 0)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -388,8 +449,13 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const uint32_t m = fl[i] & kMaskBits;
-            if (m != 0 && flagIsBulk(fl[i]))
-                fixCell<L, T, VEC, CH>(cell0 + i, a, m, i, f);
+            if (m != 0 && flagIsBulk(fl[i])) {
+                // the cell next to an x face whose only walls are across that face: operands fetched with the streaming loads
+                if (i == specAdj && m == (specSide ? XSet<L>::mask(1) : XSet<L>::mask(0)))
+                    xFixUse<L, T, VEC>(std::make_integer_sequence<int, XSet<L>::N>{}, sKeep, specSide, i, f);
+                else
+                    fixCell<L, T, VEC, CH>(cell0 + i, a, m, i, f);
+            }
         }
     }
 
@@ -478,12 +544,32 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     const int64_t cellOff = (int64_t)zm * a.pitch_z + (int64_t)y * a.pitch_y + x0;
     const T*      cell0 = reinterpret_cast<const T*>(a.in) + cellOff;
 
+    // x-face threads: the thread that owns the wall cell at x = 0 / x = nx-1 next to bulk cells (specCell = its index), and
+    // the bulk cell next to it (specAdj, side)
+    // (a thread that owns a single cell is never mixed: nothing to keep)
+    const int  specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
+    const bool rowsInside = y >= 1 && y + 1 < a.ny && zm >= 1 && zm + 1 < a.nzm;  // every neighbouring row exists
+    int        specAdj = -1, specSide = 0;
+    if (VEC > 1 && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {
+        if (x0 == 0)
+            specAdj = 1;
+        else if (x0 <= a.nx - 2 && a.nx - 2 < x0 + VEC) {
+            specAdj = a.nx - 2 - x0;
+            specSide = 1;
+        }
+    }
+    const bool xface = specCell >= 0 || specAdj >= 0;
+
     // every load of the thread goes out before anything is consumed
     uint2    s = make_uint2(0u, 0u);
     uint32_t fl[VEC];
-    if (a.flagsAlways)
+    uint32_t mapByte = 0;
+    if (a.flagMode == kFlagWords)
         ldFlags<VEC>(a.flags + cellOff, rowOk && (a.experiment != 1), fl);
-    else
+    else if (a.flagMode == kFlagCellMap) {
+        mapByte = ldPredU8(a.cellMap + row * (a.pitch_y >> 2) + (x0 >> 2), rowOk);
+        ldFlags<VEC>(a.flags + cellOff, xface, fl);  // x-face threads are special for sure: their flag words travel now
+    } else
         s = ldPredU2(a.summary + row * a.wpr + (chunk0 >> 5));
     T f[Q][VEC], edge[Q];
     loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, tx, lpr, rowOk, f, edge);
@@ -497,8 +583,6 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     // a wrong guess is ignored and any other mixed thread loads late as before.
     extern __shared__ __align__(16) unsigned char sKeepRaw[];
     T*        sKeep = reinterpret_cast<T*>(sKeepRaw) + (threadIdx.z * blockDim.y + threadIdx.y) * 32 + lane;
-    // (a thread that owns a single cell is never mixed: nothing to keep)
-    const int specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
     if (specCell >= 0) {
         // from the field's x-face cache when the caller maintains one (y-contiguous: no isolated DRAM row activations),
         // else from the wall cell's own rows
@@ -512,9 +596,15 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
         for (int q = 0; q < Q; ++q)
             cpAsync1(sKeep + q * kStepThreads, w + q * stride);
     }
+    // The bulk cell next to an x face needs, for the populations that would be pulled out of the wall, f_opp(x) + f_opp(wall
+    // cell) (finishCells).  Fetched after the flag word they were the second round trip that every warp touching an x face
+    // paid with one active lane (r01t: 22 % of the stall samples sat on the flag consumer).  Their addresses do not depend
+    // on the flags: fetch them now as well; finishCells uses them only if the cell's wall bits are exactly the x-face set.
+    if (specAdj >= 0)
+        xFixIssue<L, T, VEC>(std::make_integer_sequence<int, XSet<L>::N>{}, sKeep, cell0 + specAdj, a, specSide);
 
     bool special;
-    if (a.flagsAlways) {
+    if (a.flagMode == kFlagWords) {
         bool plain = true, bulk = false;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
@@ -527,6 +617,23 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
             return;
         }
         special = !plain;
+    } else if (a.flagMode == kFlagCellMap) {
+        const uint32_t cm = (1u << VEC) - 1u;
+        const uint32_t bulkBits = (mapByte >> (x0 & 3)) & cm, specBits = (mapByte >> (4 + (x0 & 3))) & cm;
+        if (!__any_sync(0xffffffffu, bulkBits != 0)) {
+            if (pushes)
+                faceArrive(a, face, lane);
+            return;
+        }
+        special = bulkBits != 0 && specBits != 0;
+        if (special) {
+            if (!xface)
+                ldFlags<VEC>(a.flags + cellOff, true, fl);  // late: wall-adjacent rows, obstacle surfaces
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                fl[i] = bulkBits ? kPlainBulk : ((uint32_t)NLBM_UNDEFINED << NLBM_FLAG_CLASS_SHIFT);
+        }
     } else {
         const uint32_t cm = (1u << VEC) - 1u;
         const uint32_t wbulk = (s.y >> (chunk0 & 31)) & cm;
@@ -547,7 +654,7 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     }
 
     shiftAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, tx, lpr, f, edge);
-    if (specCell >= 0)
+    if (xface)
         cpAsyncWait();  // issued with the streaming loads, which have arrived: free
     if (a.experiment == 3)  // measurement only: flags decide who is updated, but no wall fix-ups and no kept wall values
         special = false;
@@ -556,11 +663,11 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
         const int fi = pushes ? face : 0;
         T*        peerDst = (pushes && rowOk) ? reinterpret_cast<T*>(a.peer[fi]) + a.peerOff[fi] + (int64_t)y * a.pitch_y + x0 : nullptr;
         finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi], fi == 0 ? -1 : 1,
-                                 sKeep, specCell);
+                                 sKeep, specCell, specAdj, specSide);
         if (pushes)
             faceArrive(a, face, lane);
     } else {
-        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep, specCell);
+        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep, specCell, specAdj, specSide);
     }
 }
 
@@ -573,7 +680,7 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     // the wall round trip, so the tile narrows until a row has at least four pieces — never below 128 bytes per piece.
     // Whole-row warps when the row summary gates the flag loads.
     int lprLog2 = 5;
-    if (a.flagsAlways) {
+    if (a.flagMode != kFlagSummaryFirst) {
         int want = 32;
         if (rpwSel > 0) {
             want = 32 >> (rpwSel - 1);
@@ -611,8 +718,8 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     if (grid.y > 65535)
         return cudaErrorInvalidConfiguration;
     a.warpsPerFace = grid.x * grid.y * (unsigned)warps;  // every warp launched for a plane reports in
-    // one slot of Q values per thread for the speculatively fetched wall values (only x-face threads use theirs)
-    constexpr size_t keepBytes = VEC > 1 ? (size_t)COL::Q * kStepThreads * sizeof(T) : 0;
+    // one slot of Q kept values + 2 x |XSet| fix-up operands per thread for the speculative fetches (only x-face threads use theirs)
+    constexpr size_t keepBytes = VEC > 1 ? (size_t)(COL::Q + 2 * XSet<Lattice<COL::Q>>::N) * kStepThreads * sizeof(T) : 0;
     if constexpr (keepBytes > 48 * 1024) {
         static bool raised[64] = {};  // per instantiation and device; racing host threads set the same value
         int         dev = 0;

@@ -134,8 +134,22 @@ class HaloUpdateContainer(Container):
         """Waits of the peer-store transport that gave up (a neighbour never signalled); 0 for the other transports."""
         return 0 if self._ipc is None else self._ipc.timeouts()
 
-    def _run_ipc(self, streamIdx: int) -> None:
+    def _ipc_halo(self):
         from .ipc import IpcHalo
         if self._ipc is None:
             self._ipc = IpcHalo(self)
-        self._ipc.run(streamIdx)
+        return self._ipc
+
+    def _run_ipc(self, streamIdx: int) -> None:
+        self._ipc_halo().run(streamIdx)
+
+    # the two halves of an update, for schedules that push a field right after it was written and wait right before it is
+    # read (Skeleton with Options.pipelinedHalo); peer-store transport only
+    def supportsSplit(self) -> bool:
+        return self.transport == "ipc" and self.field.grid.backend.world > 1
+
+    def push(self, streamIdx: int) -> None:
+        self._ipc_halo().push(streamIdx)
+
+    def wait(self, streamIdx: int) -> None:
+        self._ipc_halo().wait(streamIdx)

@@ -62,7 +62,9 @@ class IpcHalo:
         f = halo.field
         g = f.grid
         bk = g.backend
-        self.count = 0
+        self.count = 0   # updates pushed
+        self.waited = 0  # updates waited for
+        self.counter = torch.zeros(1, dtype=torch.int32, device=bk.device)
         self.flags = torch.zeros(_FLAG_WORDS, dtype=torch.int32, device=bk.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=bk.device)
         torch.cuda.synchronize(bk.device)
@@ -110,7 +112,8 @@ class IpcHalo:
             out[nbr] = (d, first_ghost)
         return out
 
-    def run(self, streamIdx: int) -> None:
+    def push(self, streamIdx: int) -> None:
+        """Stores my boundary planes into the neighbours' ghost planes and publishes the update counter there."""
         h = self.halo
         f = h.field
         g = f.grid
@@ -121,22 +124,38 @@ class IpcHalo:
         self.count += 1
         k = self.count
         args = (f.elem_bytes, f.cardinality, h.lattice_q)
-        # push + signal
+        if not self.block:
+            # both faces and both signals in one launch
+            pu = self.peer.get(up, (None, None)) if up is not None else (None, None)
+            pd = self.peer.get(dn, (None, None)) if dn is not None else (None, None)
+            capi.call("nlbm_dense_halo_push2", C.byref(mine), f.data.data_ptr(),
+                      pu[0], g.sizes[up] if up is not None else 0, (pu[1] + 4 * FROM_BELOW) if up is not None else None,
+                      pd[0], g.sizes[dn] if dn is not None else 0, (pd[1] + 4 * FROM_ABOVE) if dn is not None else None,
+                      self.counter.data_ptr(), k, *args, st)
+            return
         for nbr, direction, slot in ((up, +1, FROM_BELOW), (dn, -1, FROM_ABOVE)):
             if nbr is None:
                 continue
             pf, pg = self.peer[nbr]
-            if self.block:
-                dd, first_ghost = self._descs[nbr]
-                capi.call("nlbm_block_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(dd), pf, first_ghost, *args, direction, st)
-            else:
-                capi.call("nlbm_dense_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(self._descs[nbr]), pf, *args, direction, st)
+            dd, first_ghost = self._descs[nbr]
+            capi.call("nlbm_block_halo_push", C.byref(mine), f.data.data_ptr(), C.byref(dd), pf, first_ghost, *args, direction, st)
             capi.call("nlbm_flag_signal", pg + 4 * slot, k, st)
-        # wait for what the neighbours pushed into my ghost planes
-        for nbr, slot in ((dn, FROM_BELOW), (up, FROM_ABOVE)):
-            if nbr is None:
-                continue
-            capi.call("nlbm_flag_wait", self.flags.data_ptr() + 4 * slot, k, TIMEOUT_MS, self.err.data_ptr(), st)
+
+    def wait(self, streamIdx: int) -> None:
+        """Holds the stream until both neighbours' pushes of the matching update arrived in my ghost planes."""
+        g = self.halo.field.grid
+        dn, up = g.neighbours()
+        self.waited += 1
+        if dn is None and up is None:
+            return
+        base = self.flags.data_ptr()
+        capi.call("nlbm_flag_wait2", (base + 4 * FROM_BELOW) if dn is not None else None, (base + 4 * FROM_ABOVE) if up is not None else None,
+                  self.waited, TIMEOUT_MS, self.err.data_ptr(), g.backend.streamHandle(streamIdx))
+
+    def run(self, streamIdx: int) -> None:
+        """A complete halo update: push, then wait for the neighbours' pushes."""
+        self.push(streamIdx)
+        self.wait(streamIdx)
 
     def timeouts(self) -> int:
         return int(self.err.item())

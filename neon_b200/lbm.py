@@ -73,6 +73,8 @@ class LbmContainers:
                       [Token(fIn, Access.READ, Pattern.STENCIL, stencilSemantic, lattice_q),
                        Token(fOut, Access.WRITE, Pattern.MAP), Token(cellTypeField, Access.READ, Pattern.MAP)], launch)
         c.halo_transport = halo_transport
+        # the next iteration stencil-reads fOut: a pipelined Skeleton pushes its faces right after the BOUNDARY kernel
+        c.push_after = [Token(fOut, Access.WRITE, Pattern.STENCIL, stencilSemantic, lattice_q)]
         return c
 
     @staticmethod
@@ -110,7 +112,8 @@ class LbmIteration:
 
     def __init__(self, stencilSemantic: StencilSemantic, occ: Occ, transfer: TransferMode, fInField: dField,
                  fOutField: dField, flagField: FlagField, omega: float, lattice_q: int = 19, compute=None,
-                 arith: int = capi.ARITH_FAST, opts: int = 0, halo_transport: str = "auto", graph: bool = False):
+                 arith: int = capi.ARITH_FAST, opts: int = 0, halo_transport: str = "auto", graph: bool = False,
+                 pipelined: bool = True):
         self.pop = [fInField, fOutField]
         self.flag, self.omega, self.parity = flagField, omega, 0
         bk = fInField.grid.backend
@@ -127,7 +130,9 @@ class LbmIteration:
             c = LbmContainers.iteration(stencilSemantic, self.pop[a], self.pop[b], flagField, omega, lattice_q, compute,
                                         arith, opts, halo_transport)
             sk = Skeleton(bk)
-            sk.sequence([c], f"LBM_{a}{b}", Options(occ, transfer), graph=graph)
+            # pipelined: iteration t pushes the faces of ITS output right after its BOUNDARY kernel, iteration t+1 only
+            # waits for them (peer-store transport; other transports keep the update in front of the consumer)
+            sk.sequence([c], f"LBM_{a}{b}", Options(occ, transfer, pipelinedHalo=pipelined), graph=graph)
             self.lbmTwoPop.append(sk)
 
     def run(self) -> None:

@@ -38,11 +38,17 @@ class Occ(Enum):
 class Options:
     occ: Occ = Occ.none
     transferMode: TransferMode = TransferMode.get
+    # Software-pipelined halo update (peer-store transport): the faces of a field are pushed into the neighbours' ghost
+    # planes right AFTER the BOUNDARY kernel that wrote them (containers name those fields in ``push_after``), and the
+    # consumer only waits for their arrival.  The transfer then overlaps the INTERNAL kernel of the SAME iteration and
+    # the next iteration never waits for the wire (the reference pulls the faces right before the consumer,
+    # multiGpuGraph.cpp:304-352, behind host-blocking syncs).
+    pipelinedHalo: bool = False
 
 
 @dataclass
 class Node:
-    kind: str  # "fork" | "join" | "halo" | "compute"
+    kind: str  # "fork" | "join" | "halo" | "halo_wait" | "halo_push" | "compute"
     name: str
     stream: int
     view: Optional[DataView] = None
@@ -58,35 +64,62 @@ class Skeleton:
         self._use_graph = False
         self._events = {}
 
+    @staticmethod
+    def _halo_of(field, semantic, transfer, lattice_q, transport):
+        """One halo-update container per (field, semantic, ...): skeletons that exchange the same field share its flags."""
+        cache = field.__dict__.setdefault("_halo_cache", {})
+        key = (semantic, transfer, lattice_q, transport)
+        if key not in cache:
+            cache[key] = field.newHaloUpdate(semantic, transfer, lattice_q, transport)
+        return cache[key]
+
     def sequence(self, operations: List[Container], name: str = "", options: Options = Options(), graph: bool = False) -> None:
         bk = self.backend
         self.name, self.options = name, options
         self.nodes = []
         multi = bk.world > 1
+        SIDE = 1  # high-priority stream: halo + BOUNDARY
         for c in operations:
             halos = []
+            transport = getattr(c, "halo_transport", "auto")
             if multi:
                 for t in c.stencilReads():
-                    halos.append(t.field.newHaloUpdate(t.semantic, options.transferMode, t.lattice_q,
-                                                       getattr(c, "halo_transport", "auto")))
+                    halos.append(self._halo_of(t.field, t.semantic, options.transferMode, t.lattice_q, transport))
+            pushes = []
+            if multi and options.pipelinedHalo and halos and all(h.supportsSplit() for h in halos):
+                for t in getattr(c, "push_after", []):
+                    pushes.append(self._halo_of(t.field, t.semantic, options.transferMode, t.lattice_q, transport))
+                if not all(h.supportsSplit() for h in pushes):
+                    pushes = []
+            pre = [Node("halo_wait", h.name, 0, DataView.STANDARD, h) for h in halos] if pushes else \
+                  [Node("halo", h.name, 0, DataView.STANDARD, h) for h in halos]
+            post = [Node("halo_push", h.name, 0, DataView.STANDARD, h) for h in pushes]
             if multi and halos and options.occ != Occ.none:
+                # the side stream's nodes are issued FIRST and run at high priority: BOUNDARY and the face traffic are
+                # out of the way while INTERNAL still fills the chip (round 1 issued INTERNAL first: the side stream's
+                # work then ran in INTERNAL's tail and OCC bought nothing, profiles/r01l)
                 self.nodes.append(Node("fork", "fork", 0))
+                for n in pre + [Node("compute", c.name, SIDE, DataView.BOUNDARY, c)] + post:
+                    n.stream = SIDE
+                    self.nodes.append(n)
                 self.nodes.append(Node("compute", c.name, 0, DataView.INTERNAL, c))
-                for h in halos:
-                    self.nodes.append(Node("halo", h.name, 1, DataView.STANDARD, h))
-                self.nodes.append(Node("compute", c.name, 1, DataView.BOUNDARY, c))
                 self.nodes.append(Node("join", "join", 0))
             else:
-                for h in halos:
-                    self.nodes.append(Node("halo", h.name, 0, DataView.STANDARD, h))
-                self.nodes.append(Node("compute", c.name, 0, DataView.STANDARD, c))
+                self.nodes += pre + [Node("compute", c.name, 0, DataView.STANDARD, c)] + post
         bk.setAvailableStreamSet(1 + max((n.stream for n in self.nodes), default=0))
         self._use_graph = bool(graph) and not multi and bk.runtime == Runtime.stream
         self._graph = None
+        cuda = bk.runtime == Runtime.stream
+        self._ev_fork = bk.newEvent() if cuda else None  # created once: an iteration allocates nothing
+        self._ev_join = bk.newEvent() if cuda else None
 
     def halos(self):
-        """The halo-update containers this sequence inserted."""
-        return [n.container for n in self.nodes if n.kind == "halo"]
+        """The halo-update containers this sequence uses."""
+        out = []
+        for n in self.nodes:
+            if n.kind.startswith("halo") and n.container not in out:
+                out.append(n.container)
+        return out
 
     def schedule(self):
         """[(stream, kind, name, view)] in host issue order — what DB_multiGpuGraph.dot shows in the reference."""
@@ -98,14 +131,19 @@ class Skeleton:
         for n in self.nodes:
             if n.kind == "fork":
                 if cuda:
-                    e = bk.newEvent()
-                    e.record(bk.stream(0))
-                    bk.stream(1).wait_event(e)
+                    self._ev_fork.record(bk.stream(0))
+                    bk.stream(1).wait_event(self._ev_fork)
             elif n.kind == "join":
                 if cuda:
-                    e = bk.newEvent()
-                    e.record(bk.stream(1))
-                    bk.stream(0).wait_event(e)
+                    self._ev_join.record(bk.stream(1))
+                    bk.stream(0).wait_event(self._ev_join)
+            elif n.kind == "halo_wait":
+                ipc = n.container._ipc_halo()
+                if ipc.count == ipc.waited:  # nobody pushed the update this wait is for (first run): do it now
+                    n.container.push(n.stream)
+                n.container.wait(n.stream)
+            elif n.kind == "halo_push":
+                n.container.push(n.stream)
             else:
                 n.container.run(n.stream, n.view)
 

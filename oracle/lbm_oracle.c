@@ -16,6 +16,12 @@
 #include <stdint.h>
 #include <string.h>
 
+/* threads used by the step loops: 1 by default (the scalar port that bench.py may time as "cores": 1);
+ * tests raise it so that hundreds of iterations finish in seconds — results are bit-identical. */
+static int g_olbm_threads = 1;
+void       olbm_set_threads(int n) { g_olbm_threads = n < 1 ? 1 : n; }
+int        olbm_get_threads(void) { return g_olbm_threads; }
+
 enum { OLBM_BOUNCE = 0, OLBM_MOVING = 1, OLBM_BULK = 2 }; /* src/CellType.h:5-11 */
 
 /* benchmarks/lbm-lid-driven-cavity-flow/src/D3Q19.h:23-44 (velocities), :112-132 (weights) */

@@ -101,6 +101,8 @@ void SFX(olbm_d3q19_step)(int nx, int ny, int nz, const STORE* fin, STORE* fout,
 {
     const size_t  cells = (size_t)nx * ny * nz;
     const COMPUTE omega = (COMPUTE)omega_d; /* Config.h:62 getLbmParameters<ComputeFP> */
+    /* cells are independent (two fields): threads over z give the same bits, only sooner (long-run parity tests) */
+#pragma omp parallel for schedule(static) if (g_olbm_threads > 1) num_threads(g_olbm_threads > 1 ? g_olbm_threads : 1)
     for (int z = 0; z < nz; ++z)
         for (int y = 0; y < ny; ++y)
             for (int x = 0; x < nx; ++x) {
@@ -126,6 +128,7 @@ void SFX(olbm_d3q27_step)(int nx, int ny, int nz, const STORE* fin, STORE* fout,
 {
     const size_t cells = (size_t)nx * ny * nz;
     const STORE  omega = (STORE)omega_d;
+#pragma omp parallel for schedule(static) if (g_olbm_threads > 1) num_threads(g_olbm_threads > 1 ? g_olbm_threads : 1)
     for (int z = 0; z < nz; ++z)
         for (int y = 0; y < ny; ++y)
             for (int x = 0; x < nx; ++x) {

@@ -40,6 +40,13 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_threads(n: int = 0) -> int:
+    """Threads of the step loops (0 = all host cores).  The results do not depend on it."""
+    n = n or (os.cpu_count() or 1)
+    lib().olbm_set_threads(C.c_int(n))
+    return n
+
+
 def _p(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 

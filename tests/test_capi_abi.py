@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported(capi):
 
 
 def test_abi_version_and_layout(capi):
-    assert capi.lib().nlbm_abi_version() == 2
+    assert capi.lib().nlbm_abi_version() == 3
     d = capi.DenseDesc()
     d.nx, d.ny, d.nz_local, d.z_halo = 100, 7, 5, 1
     pb, fb = C.c_size_t(), C.c_size_t()

@@ -107,6 +107,54 @@ def test_parity_with_oracle(nb, bk, oracle, q, store, compute, dim, geom, iters)
         assert np.array_equal(v.view(np.uint8), ref.view(np.uint8)), f"vec={vec}"
 
 
+def _cluttered_cavity(oracle, dim, seed, density=0.08):
+    """Cavity with random bounce-back / moving-wall cells in the interior, many of them right next to the x faces: the
+    cells at x = 1 and x = nx-2 carry every kind of wall-bit pattern, so the speculative x-face fix-up of the direct kernel
+    is taken, refused and mixed with the late path within one warp."""
+    nx, ny, nz = dim
+    cls = oracle.classify(0, nx, ny, nz)
+    rng = np.random.default_rng(seed)
+    inner = cls[1:-1, 1:-1, 1:-1]
+    r = rng.random(inner.shape)
+    inner[r < density] = 0        # bounce-back obstacle cells
+    inner[r > 1.0 - 0.02] = 1     # a few moving-wall cells (non-zero wall populations)
+    col = rng.random((nz - 2, ny - 2)) < 0.3
+    inner[:, :, 1][col] = 0       # x = 2 solid: the cell at x = 1 then has walls on both sides along x
+    inner[:, :, -2][col.T[: ny - 2, : nz - 2].T] = 0
+    return cls
+
+
+VARIANTS = [0, "OPT_FLAG_WORDS", "OPT_FLAGS_SUMMARY_FIRST", "OPT_NO_XFACE_FIXUP_PREFETCH", "OPT_NO_XFACE_PREFETCH",
+            ("OPT_FLAG_WORDS", "OPT_NO_XFACE_FIXUP_PREFETCH", "OPT_NO_XFACE_PREFETCH")]
+
+
+@pytest.mark.parametrize("q,store,dim", [(19, np.float32, (136, 22, 18)), (19, np.float32, (64, 16, 12)), (27, np.float64, (70, 14, 12)),
+                                         (19, np.float64, (37, 12, 11)), (27, np.float32, (131, 10, 9))])
+def test_kernel_variants_agree_bit_for_bit(nb, bk, oracle, q, store, dim):
+    """Every way the direct kernel learns about its cells (cell map / flag words / row summary) and every speculative fetch
+    (kept wall values, x-face fix-up operands) switched on or off: the same bits as the oracle, on the cavity, on the inlet
+    geometry (non-zero populations in the x = 0 wall) and on a cavity cluttered with obstacles next to the x faces."""
+    for geom in (0, 2, "clutter"):
+        nx, ny, nz = dim
+        cls = _cluttered_cavity(oracle, dim, 7) if geom == "clutter" else oracle.classify(geom, nx, ny, nz)
+        mask = oracle.wall_mask(q, cls)
+        pop = oracle.init_pop(q, cls, store)
+        # wall populations that differ from cell to cell: a wrong operand cannot cancel
+        rng = np.random.default_rng(3)
+        noise = (rng.random(pop.shape) * 0.01).astype(store)
+        pop = np.where(np.broadcast_to(cls != nb.BULK, pop.shape), pop + noise, pop).astype(store)
+        omega, iters = 1.3, 5
+        ref = oracle.run(q, pop, cls, mask, omega, iters)
+        for var in VARIANTS:
+            names = var if isinstance(var, tuple) else ((var,) if var else ())
+            opts = nb.opt_kernel(nb.KERNEL_DIRECT)
+            for n in names:
+                opts |= getattr(nb, n)
+            out, flag = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, opts=opts)
+            assert np.array_equal(flag.masks(), mask)
+            assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), f"geom {geom} variant {var}"
+
+
 def test_device_setup_matches_oracle(nb, bk, oracle):
     """nlbm_dense_classify / wall_mask / init_pop against the oracle, bit for bit, all geometries."""
     from neon_b200 import problems as P

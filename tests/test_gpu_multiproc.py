@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, results, transport="ipc"):
+def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, results, transport="ipc", pipelined=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -38,7 +38,10 @@ def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, result
         grid = nb.dGrid(bk, dim) if kind == "dGrid" else nb.bGrid(bk, dim)
         pop0, pop1, flag = P.setup_device(grid, q, dtype, P.CAVITY_SPHERE)
         it = nb.LbmIteration(nb.StencilSemantic.streaming, getattr(nb.Occ, occ_name), nb.TransferMode.get, pop0, pop1, flag, 1.25,
-                             lattice_q=q, arith=nb.ARITH_REFERENCE, halo_transport=transport)
+                             lattice_q=q, arith=nb.ARITH_REFERENCE, halo_transport=transport, pipelined=pipelined)
+        if transport == "ipc":
+            kinds = [k for _, k, _, _ in it.lbmTwoPop[0].schedule()]
+            assert ("halo_push" in kinds and "halo_wait" in kinds) == pipelined and ("halo" in kinds) == (not pipelined), kinds
         for _ in range(iters):
             it.run()
         bk.syncAll()
@@ -52,16 +55,19 @@ def _worker(rank, world, port, q, dtype_name, dim, iters, occ_name, kind, result
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("q,dtype,world,occ,kind", [(19, "float32", 2, "standard", "dGrid"), (19, "float32", 3, "none", "dGrid"),
-                                                     (27, "float64", 2, "standard", "dGrid"), (19, "float32", 2, "standard", "bGrid"),
-                                                     (27, "float64", 2, "none", "bGrid")])
-def test_ipc_halo_across_processes(oracle, q, dtype, world, occ, kind):
+@pytest.mark.parametrize("q,dtype,world,occ,kind,pipelined", [
+    (19, "float32", 2, "standard", "dGrid", True), (19, "float32", 3, "none", "dGrid", True), (19, "float32", 3, "standard", "dGrid", True),
+    (27, "float64", 2, "standard", "dGrid", True), (19, "float32", 2, "standard", "bGrid", True), (27, "float64", 2, "none", "bGrid", True),
+    (19, "float32", 2, "standard", "dGrid", False), (19, "float32", 3, "none", "dGrid", False), (19, "float32", 2, "standard", "bGrid", False)])
+def test_ipc_halo_across_processes(oracle, q, dtype, world, occ, kind, pipelined):
+    """pipelined: faces pushed right after the BOUNDARY kernel that computed them, the consumer only waits (Options.pipelinedHalo);
+    otherwise the whole update sits in front of the consumer, as the reference schedules it."""
     if not torch.cuda.is_available():
         pytest.fail("gpu tests need a CUDA device")
     dim, iters = ((36, 20, 23) if kind == "dGrid" else (36, 20, 37)), 8
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), q, dtype, dim, iters, occ, kind, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), q, dtype, dim, iters, occ, kind, results, "ipc", pipelined), nprocs=world, join=True)
     nx, ny, nz = dim
     cls = oracle.classify(1, nx, ny, nz)
     mask = oracle.wall_mask(q, cls)

@@ -113,9 +113,10 @@ def _worker(rank, world, port, semantic, q, results):
         g = grid.newField("out", q, np.float32)
         it = nb.LbmIteration(sem, nb.Occ.standard, nb.TransferMode.get, f, g, flag, 1.0, lattice_q=q)
         sched = it.lbmTwoPop[0].schedule()
-        # OCC: INTERNAL on stream 0, halo + BOUNDARY on stream 1, joined (multiGpuGraph.cpp:120-143, 304-352)
-        assert [(s, k, v) for s, k, _, v in sched] == [(0, "fork", None), (0, "compute", "INTERNAL"), (1, "halo", "STANDARD"),
-                                                       (1, "compute", "BOUNDARY"), (0, "join", None)]
+        # OCC: INTERNAL on stream 0, halo + BOUNDARY on stream 1, joined (multiGpuGraph.cpp:120-143, 304-352); the side
+        # stream's nodes are issued first (they run at high priority while INTERNAL fills the chip)
+        assert [(s, k, v) for s, k, _, v in sched] == [(0, "fork", None), (1, "halo", "STANDARD"), (1, "compute", "BOUNDARY"),
+                                                       (0, "compute", "INTERNAL"), (0, "join", None)]
         none = nb.Skeleton(bk)
         none.sequence([nb.LbmContainers.iteration(sem, f, g, flag, 1.0, q)], "noOcc", nb.Options(nb.Occ.none, nb.TransferMode.get))
         assert [(s, k, v) for s, k, _, v in none.schedule()] == [(0, "halo", "STANDARD"), (0, "compute", "STANDARD")]

@@ -190,3 +190,68 @@ def test_fused_step_push_orders_every_hazard(world, nz):
 def test_fused_broken_variants_are_caught():
     assert fused_run(3, 4, wait_before_launch=False) != []
     assert fused_run(3, 4, signal_after_plane=False) != []   # the counter must be published by the LAST warp of the plane
+
+
+# ------------------------------------------------------------------------------------------------ pipelined halo (round 2)
+def pipelined_run(world, nz, occ, iters=7, signal_after_push=True, wait_before_boundary=True, push_after_boundary=True):
+    """Skeleton with Options.pipelinedHalo (neon_b200/skeleton.py): iteration t waits for the faces of ITS INPUT field (pushed by
+    the neighbours right after their BOUNDARY kernel of iteration t-1; at t = 0 every rank pushes them first), runs BOUNDARY
+    (high-priority side stream, issued before INTERNAL), then pushes the faces of its OUTPUT field and publishes the field's
+    update counter in the neighbours' flag words.  Each field has its own flag words and counters."""
+    m = Model()
+    pushed = {}   # (rank, field) -> updates pushed
+    waited = {}
+
+    def push(r, s, f):
+        pushed[(r, f)] = k = pushed.get((r, f), 0) + 1
+        for x in (r + 1, r - 1):
+            if not 0 <= x < world:
+                continue
+            src, dst = (nz - 1, LO) if x > r else (0, HI)
+            slot = (f, "from_below" if x > r else "from_above")
+            if not signal_after_push:
+                m.signal(r, s, x, slot, k)
+            m.op(r, s, f"push f{f} #{k}", {(r, f, src)}, {(x, f, dst)})
+            if signal_after_push:
+                m.signal(r, s, x, slot, k)
+
+    def wait(r, s, f):
+        waited[(r, f)] = k = waited.get((r, f), 0) + 1
+        for x in (r + 1, r - 1):
+            if 0 <= x < world:
+                m.wait(r, s, (f, "from_below" if x < r else "from_above"), k)
+
+    for t in range(iters):
+        fin, fout = t % 2, 1 - t % 2
+        for r in range(world):
+            hs = 1 if occ == "standard" else 0
+            if occ == "standard":
+                m.fork(r)
+            if pushed.get((r, fin), 0) == waited.get((r, fin), 0):
+                push(r, hs, fin)
+            if wait_before_boundary:
+                wait(r, hs, fin)
+            view = sorted({0, nz - 1}) if occ == "standard" else range(nz)
+            if not push_after_boundary:
+                push(r, hs, fout)
+            m.op(r, hs, "BOUNDARY" if occ == "standard" else "STANDARD", {(r, fin, p) for p in planes_read(nz, view)},
+                 {(r, fout, z) for z in view})
+            if push_after_boundary:
+                push(r, hs, fout)
+            if occ == "standard":
+                m.op(r, 0, "INTERNAL", {(r, fin, p) for p in planes_read(nz, range(1, nz - 1))}, {(r, fout, z) for z in range(1, nz - 1)})
+                m.join(r)
+    return m.unordered_hazards()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("occ", ["none", "standard"])
+@pytest.mark.parametrize("nz", [2, 3, 6])
+def test_pipelined_halo_orders_every_hazard(world, occ, nz):
+    assert pipelined_run(world, nz, occ) == []
+
+
+def test_pipelined_broken_variants_are_caught():
+    assert pipelined_run(3, 4, "standard", signal_after_push=False) != []    # flag published before the data
+    assert pipelined_run(3, 4, "none", wait_before_boundary=False) != []     # nobody waits for the neighbours' faces
+    assert pipelined_run(3, 4, "standard", push_after_boundary=False) != []  # faces pushed before they were computed

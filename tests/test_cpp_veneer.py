@@ -166,6 +166,21 @@ def test_d3q27_against_the_oracle(app, tmp_path, oracle, fp, parts):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,fp,geom,grid", [("d3q27_sphere16_f64_cfgomega", "double", "sphere", "dGrid"),
+                                               ("d3q27_cavity16_f32_cfgomega", "float", "cavity", "dGrid"),
+                                               ("d3q27_sphere16_f64_cfgomega", "double", "sphere", "bGrid")])
+def test_d3q27_against_reference_compiled_dumps(app, tmp_path, golden_dir, name, fp, geom, grid):
+    """D3Q27 through the C++ benchmark app against dumps of the reference's OWN D3Q27 kernels (apps/lbmMultiRes stream /
+    collideBGK, compiled unmodified by oracle/Makefile.ref27), omega as Config.cpp:105-111 computes it for N = 16."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    d = _dump(app, str(tmp_path), (16, 16, 16), fp, geom, int(g["iters"]), extra=("--grid", grid), lattice="D3Q27")
+    if fp == "double":
+        assert d["omega"] == float(g["omega"])
+    assert np.array_equal(d["cls"], g["cls"]) and np.array_equal(d["mask"], g["mask"])
+    assert np.array_equal(d["pop"].view(np.uint8), g["pop"].view(np.uint8))
+
+
+@pytest.mark.gpu
 def test_visual_mode_profiles_match_the_stock_reference_run(app, tmp_path):
     """Known answers of the UNMODIFIED reference's --visual run, N=64 fp32, state after 100 iterations."""
     run_app(app, ["--deviceType", "gpu", "--deviceIds", "0", "--domain-size", "64", "--max-iter", "101", "--computeFP", "float",

@@ -56,13 +56,14 @@ def run_block(nb, bk, q, dtype, cls, pop, omega, iters, arith, active=None):
 def test_golden_reference_dumps_on_bgrid(nb, bk, golden_dir, name):
     from neon_b200 import problems as P
     g = np.load(os.path.join(golden_dir, name + ".npz"))
+    q = int(g["q"]) if "q" in g else 19
     cls, ref = g["cls"], g["pop"]
-    pop = P.host_populations(19, cls, ref.dtype, float(g["ulb"]))
-    out, flag, _ = run_block(nb, bk, 19, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_REFERENCE)
+    pop = P.host_populations(q, cls, ref.dtype, float(g["ulb"]))
+    out, flag, _ = run_block(nb, bk, q, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_REFERENCE)
     assert np.array_equal(flag.masks(), g["mask"])
     assert np.array_equal(flag.classes(), cls)
     assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
-    fast, _, _ = run_block(nb, bk, 19, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_FAST)
+    fast, _, _ = run_block(nb, bk, q, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_FAST)
     assert rel_err(fast, ref) < REL_TOL[ref.dtype]
 
 

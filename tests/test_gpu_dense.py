@@ -56,13 +56,16 @@ def test_golden_reference_dumps(nb, bk, golden_dir, name):
     """Populations / masks dumped by the UNMODIFIED reference (oracle/make_golden.py): REFERENCE mode is bit-exact."""
     from neon_b200 import problems as P
     g = np.load(os.path.join(golden_dir, name + ".npz"))
+    q = int(g["q"]) if "q" in g else 19  # d3q27_*: the reference's apps/lbmMultiRes kernels (oracle/ref_driver27.cu)
     cls, ref = g["cls"], g["pop"]
-    pop = P.host_populations(19, cls, ref.dtype, float(g["ulb"]))
-    out, flag = run_cuda(nb, bk, 19, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_REFERENCE)
-    assert np.array_equal(flag.masks(), g["mask"])
-    assert np.array_equal(flag.classes(), cls)
-    assert np.array_equal(out.view(np.uint8), ref.view(np.uint8))
-    fast, _ = run_cuda(nb, bk, 19, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_FAST)
+    pop = P.host_populations(q, cls, ref.dtype, float(g["ulb"]))
+    for kern in (nb.KERNEL_DIRECT, nb.KERNEL_TMA):
+        out, flag = run_cuda(nb, bk, q, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_REFERENCE,
+                             opts=nb.opt_kernel(kern))
+        assert np.array_equal(flag.masks(), g["mask"])
+        assert np.array_equal(flag.classes(), cls)
+        assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), f"kernel {kern}"
+    fast, _ = run_cuda(nb, bk, q, ref.dtype, cls, pop, float(g["omega"]), int(g["iters"]), nb.ARITH_FAST)
     assert rel_err(fast, ref) < REL_TOL[ref.dtype]
 
 

@@ -70,6 +70,11 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * tolerance (1e-5 relative fp32, 1e-12 fp64), not bitwise.                       */
 #define NLBM_ARITH_REFERENCE 0
 #define NLBM_ARITH_FAST 1
+/* REFERENCE arithmetic for D3Q19 fp32 is evaluated by default through a re-arrangement that performs every rounding of the
+ * reference expressions on the same exact value (same bits, proven per merge in csrc/lbm_collide_exact.cuh) with a third
+ * of the float<->double conversions; this bit selects the operand-for-operand transcription instead.  Never changes
+ * results.                                                                       */
+#define NLBM_OPT_REF_LITERAL (1 << 30)
 /* Tuning (bits 4..7: cells per thread along x, 0 = library default; bits 8..11:
  * log2 of rows per block, 0 = default).  Never changes results.                  */
 #define NLBM_OPT_VEC(v) (((v)&0xF) << 4)
@@ -169,7 +174,17 @@ int nlbm_dense_wall_cache_build(const nlbm_dense_desc* d, int q, int elem_bytes,
  * Writes the class bits of every plane including ghosts (mask bits cleared).       */
 int nlbm_dense_classify(const nlbm_dense_desc* d, int geom, const double* sphere, void* stream);
 /* Rebuilds the per-row summary and the cell map from the flag words (after the caller wrote them itself). */
+/* Self-test of the two exact building blocks of that evaluation (synchronous, current device; used by tests/):
+ * kind 0: float -> double by integer multiply-add against the conversion instruction for EVERY positive normal float;
+ * kind 1: the shared-reciprocal division against IEEE division on n pseudo-random operand sets inside its guard.
+ * *mismatches receives the number of differing results (must be 0).                                              */
+int nlbm_selftest_exact(int kind, uint64_t n, uint64_t seed, uint64_t* mismatches);
 int nlbm_dense_flags_commit(const nlbm_dense_desc* d, void* stream);
+/* Flag words from a host-made classification (FieldBase::updateDeviceData of the CellType field, RunCavityTwoPop.cu:226-233):
+ * `classes` (DEVICE pointer) holds one byte per cell, dense [nplanes][ny][nx], for the memory planes
+ * [zm_first, zm_first + nplanes); every other plane and the row padding become `undefined`; wall bits are cleared;
+ * summary and cell map are rebuilt.  4 x less to upload than flag words.                                      */
+int nlbm_dense_flags_from_classes(const nlbm_dense_desc* d, const uint8_t* classes, int zm_first, int nplanes, void* stream);
 /* LbmContainers::computeWallNghMask, LbmTools.h:344-376 (bit-exact).  q = 19|27.
  * Needs valid class bits in the ghost planes.  *d_bad (device int32, may be NULL) is
  * incremented for every bulk-cell neighbour outside the global domain.             */

@@ -4,7 +4,7 @@ Only what the path needs: the C-ABI kernel library (csrc/ -> lib/libneon_lbm.so,
 mirror of the reference interface for it (Backend, dGrid/dField, Container, Skeleton with OCC, LbmIteration).
 """
 from ._capi import (ARITH_FAST, ARITH_REFERENCE, BOUNCE_BACK, BULK, KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, MOVING_WALL, UNDEFINED,
-                    NeonException, OPT_FLAG_WORDS, OPT_FLAGS_SUMMARY_FIRST, OPT_NO_XFACE_FIXUP_PREFETCH, OPT_NO_XFACE_PREFETCH,
+                    NeonException, OPT_FLAG_WORDS, OPT_REF_LITERAL, OPT_FLAGS_SUMMARY_FIRST, OPT_NO_XFACE_FIXUP_PREFETCH, OPT_NO_XFACE_PREFETCH,
                     opt_kernel, opt_rows_log2, opt_vec)
 from .backend import Backend, Runtime
 from .bgrid import bField, bFlagField, bGrid

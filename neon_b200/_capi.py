@@ -44,6 +44,7 @@ OPT_FLAGS_SUMMARY_FIRST = 1 << 20
 OPT_NO_XFACE_PREFETCH = 1 << 27
 OPT_FLAG_WORDS = 1 << 28
 OPT_NO_XFACE_FIXUP_PREFETCH = 1 << 29
+OPT_REF_LITERAL = 1 << 30  # REFERENCE arithmetic: operand-for-operand transcription instead of the conversion-lean evaluation
 
 
 class NeonException(RuntimeError):
@@ -105,6 +106,8 @@ _SIGNATURES = {
     "nlbm_dense_wall_cache_build": (C.c_int, [_D, C.c_int, C.c_int, _P]),
     "nlbm_dense_classify": (C.c_int, [_D, C.c_int, C.POINTER(C.c_double), _P]),
     "nlbm_dense_flags_commit": (C.c_int, [_D, _P]),
+    "nlbm_selftest_exact": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "nlbm_dense_flags_from_classes": (C.c_int, [_D, _P, C.c_int, C.c_int, _P]),
     "nlbm_dense_wall_mask": (C.c_int, [_D, C.c_int, _P, _P]),
     "nlbm_dense_init_pop_f32": (C.c_int, [_D, C.c_int, C.c_double, _P]),
     "nlbm_dense_init_pop_f64": (C.c_int, [_D, C.c_int, C.c_double, _P]),

@@ -202,6 +202,27 @@ class bField(_BlockFieldBase):
         blocks = g._gather_blocks(np.asarray(host, self.dtype))
         self.view3[:, :g.n_blocks_alloc].copy_(torch.from_numpy(blocks), non_blocking=False)
 
+    # host mirror kept in the field's own layout [cardinality, blocks, 512] (what Neon's bField host mirror is): no
+    # re-ordering on either side of the bus
+    def updateDeviceBlocks(self, host: torch.Tensor, stream_idx: int = 0) -> None:
+        """``host`` (pinned for an asynchronous copy): [cardinality, n_blocks_alloc, 512], local blocks then ghost blocks."""
+        g = self.grid
+        assert tuple(host.shape) == (self.cardinality, g.n_blocks_alloc, BLOCK_CELLS), host.shape
+        with torch.cuda.stream(g.backend.stream(stream_idx)):
+            self.view3[:, :g.n_blocks_alloc].copy_(host, non_blocking=True)
+
+    def updateHostBlocksInto(self, host: torch.Tensor, stream_idx: int = 0) -> None:
+        """Asynchronous device -> host copy of the LOCAL blocks into ``host[:, :n_blocks]``."""
+        g = self.grid
+        with torch.cuda.stream(g.backend.stream(stream_idx)):
+            host[:, :g.n_blocks].copy_(self.view3[:, :g.n_blocks], non_blocking=True)
+
+    def copyFrom(self, other: "bField", stream_idx: int = 0) -> None:
+        """Device-to-device copy of another field of the same grid and shape (ghost blocks included)."""
+        assert other.grid is self.grid and other.cardinality == self.cardinality and other.dtype == self.dtype
+        with torch.cuda.stream(self.grid.backend.stream(stream_idx)):
+            self.data.copy_(other.data, non_blocking=True)
+
     def updateHostData(self) -> np.ndarray:
         """Global dense array [cardinality, nz, ny, nx] holding this rank's local blocks (zeros elsewhere)."""
         g = self.grid

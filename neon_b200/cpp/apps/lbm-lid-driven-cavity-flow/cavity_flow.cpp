@@ -19,6 +19,7 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -395,6 +396,9 @@ void run(Config& config, RunReport& report)
     std::cout << "Metrics:\n    Problem Setup: " << report.setupTime.back() << " microseconds" << std::endl;
 
     // ---- --visual: rho/u export every 100 iterations (RunCavityTwoPop.cu:82-150) --------------------------------------
+    // one halo-update container per population field, built on first use and kept (a fresh one every export would leave
+    // its events with the Backend until the end of the run)
+    std::map<size_t, Neon::set::Container> visualHalo;
     auto exportRhoAndU = [&](int iterationId) {
         if constexpr (Lattice::Q == 19 && std::is_same_v<Grid, Neon::dGrid>) {
             if (iterationId % 100 != 0) {
@@ -402,8 +406,11 @@ void run(Config& config, RunReport& report)
             }
             auto& f = iteration.getInput();
             bk.syncAll();
-            f.newHaloUpdate(Neon::set::StencilSemantic::standard, Neon::set::TransferMode::get, Neon::Execution::device)
-                .run(Neon::Backend::mainStreamIdx);
+            if (!visualHalo.count(f.getUid())) {
+                visualHalo.emplace(f.getUid(), f.newHaloUpdate(Neon::set::StencilSemantic::standard, Neon::set::TransferMode::get,
+                                                               Neon::Execution::device));
+            }
+            visualHalo.at(f.getUid()).run(Neon::Backend::mainStreamIdx);
             bk.syncAll();
             Tools::computeRhoAndU(f, flag, rho, u).run(Neon::Backend::mainStreamIdx);
             u.updateHostData(Neon::Backend::mainStreamIdx);

@@ -227,17 +227,56 @@ struct LbmContainers
             NEON_THROW_UNSUPPORTED_OPERATION("the wall mask is built in place (RunCavityTwoPop.cu:239)");
         }
         const Neon::Backend bk = infoInField.getBackend();
-        return Neon::set::Container::factoryDeviceManaged(
+        /* one error counter per device, allocated once with the container (device word + pinned host word): a run enqueues
+         * memset, kernel and read-back on every device first and only then waits — no allocation, no per-device host sync */
+        struct Counters
+        {
+            Neon::Backend         bk;
+            std::vector<int32_t*> dev, host;
+            ~Counters()
+            {
+                for (size_t d = 0; d < dev.size(); ++d) {
+                    bk.setDevice(int(d));
+                    if (dev[d]) {
+                        cudaFree(dev[d]);
+                    }
+                    if (host[d]) {
+                        cudaFreeHost(host[d]);
+                    }
+                }
+            }
+        };
+        auto cnt = std::make_shared<Counters>();
+        cnt->bk = bk;
+        cnt->dev.assign(bk.getDeviceCount(), nullptr);
+        cnt->host.assign(bk.getDeviceCount(), nullptr);
+        for (int d = 0; d < bk.getDeviceCount(); ++d) {
+            bk.setDevice(d);
+            NEON_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&cnt->dev[d]), sizeof(int32_t)));
+            NEON_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&cnt->host[d]), sizeof(int32_t)));
+            *cnt->host[d] = 0;
+        }
+        auto check = [cnt, bk](int dev, int streamIdx) {
+            bk.setDevice(dev);
+            NEON_CUDA_CHECK(cudaStreamSynchronize(bk.stream(dev, streamIdx)));
+            const int32_t nBad = *cnt->host[dev];
+            if (nBad != 0) {
+                Neon::NeonException e("computeWallNghMask");
+                e << nBad << " bulk-cell neighbours fall outside the domain: enclose the geometry with non-bulk cells";
+                NEON_THROW(e);
+            }
+        };
+        auto pending = std::make_shared<std::vector<char>>(bk.getDeviceCount(), 0);
+        auto c = Neon::set::Container::factoryDeviceManaged(
             "LBM_computeWallNghMask", bk, [&](Neon::SetIdx setIdx, Neon::set::Loader& L) {
-                auto            in = L.load(infoInField, Neon::Pattern::STENCIL);
+                auto in = L.load(infoInField, Neon::Pattern::STENCIL);
                 auto out = L.load(infoOutpeField);
                 auto d = out.desc; /* nlbm_dense_desc or nlbm_block_desc */
                 d.flags = out.mem();
                 (void)in;
                 const int dev = setIdx.idx;
                 return [=](int streamIdx, Neon::DataView) {
-                    int32_t* bad = nullptr;
-                    NEON_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&bad), sizeof(int32_t)));
+                    int32_t*     bad = cnt->dev[dev];
                     cudaStream_t st = bk.stream(dev, streamIdx);
                     NEON_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
                     if constexpr (std::is_same_v<decltype(d), nlbm_block_desc>) {
@@ -245,17 +284,20 @@ struct LbmContainers
                     } else {
                         Neon::detail::check(nlbm_dense_wall_mask(&d, Lattice::Q, bad, st), "nlbm_dense_wall_mask");
                     }
-                    int32_t nBad = 0;
-                    NEON_CUDA_CHECK(cudaMemcpyAsync(&nBad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                    NEON_CUDA_CHECK(cudaStreamSynchronize(st));
-                    cudaFree(bad);
-                    if (nBad != 0) {
-                        Neon::NeonException e("computeWallNghMask");
-                        e << nBad << " bulk-cell neighbours fall outside the domain: enclose the geometry with non-bulk cells";
-                        NEON_THROW(e);
-                    }
+                    NEON_CUDA_CHECK(cudaMemcpyAsync(cnt->host[dev], bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                    (*pending)[dev] = 1;
                 };
             });
+        /* the geometry check needs the counters on the host: after ALL devices were issued (all-device run) */
+        c.template as<Neon::set::detail::DeviceManagedImpl>()->afterAll = [=](int streamIdx) {
+            for (int d = 0; d < int(pending->size()); ++d) {
+                if ((*pending)[d]) {
+                    (*pending)[d] = 0;
+                    check(d, streamIdx);
+                }
+            }
+        };
+        return c;
     }
 
     /* LbmTools.h:384-437 (D3Q19): rho and u of every cell from the populations */

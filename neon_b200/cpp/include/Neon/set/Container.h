@@ -79,6 +79,8 @@ class Container
         virtual void run(int streamIdx, DataView dataView) = 0;
         /* per-device variant (Container::run(SetIdx, streamIdx, dataView), DeviceContainer.h:118-150) */
         virtual void run(int setIdx, int streamIdx, DataView dataView) = 0;
+        /* false if running the container changes host-side state that a replayed CUDA graph would not repeat */
+        virtual bool graphSafe() const { return true; }
     };
 
     Container() = default;
@@ -94,6 +96,7 @@ class Container
         need();
         mImpl->run(setIdx.idx, streamIdx, dataView);
     }
+    bool                      graphSafe() const { return need()->graphSafe(); }
     const std::string&        getName() const { return need()->name; }
     Kind                      getKind() const { return need()->kind; }
     const std::vector<Token>& getTokens() const { return need()->tokens; }
@@ -168,19 +171,20 @@ struct DeviceManagedImpl : Container::Impl
 {
     std::vector<std::function<void(int, DataView)>> launchers; /* one per device */
     bool                                            genericBody = false; /* user lambda: may write anything it loaded non-const */
+    /* optional: called once after every device has been issued (all-device run only) — e.g. to read back and check
+     * per-device error counters without serialising the devices behind host syncs */
+    std::function<void(int)> afterAll;
     void run(int streamIdx, DataView dataView) override
     {
-        if (genericBody) {
-            for (const auto& t : tokens) {
-                if (t.access == Access::write && t.onGenericWrite) {
-                    t.onGenericWrite();
-                }
-            }
-        }
         for (int d = 0; d < int(launchers.size()); ++d) {
             run(d, streamIdx, dataView);
         }
+        if (afterAll) {
+            afterAll(streamIdx);
+        }
     }
+    /* both entry points pass here: a user lambda that writes a population field makes that field's x-face cache stale
+     * whichever way it was launched (DeviceContainer.h:118-150 lets callers run one device at a time) */
     void run(int setIdx, int streamIdx, DataView dataView) override
     {
         if (backend.runtime() != Runtime::stream) {
@@ -188,8 +192,29 @@ struct DeviceManagedImpl : Container::Impl
             e << "compute containers need Runtime::stream: there is no CPU fallback behind this veneer";
             NEON_THROW(e);
         }
+        if (genericBody) {
+            for (const auto& t : tokens) {
+                if (t.access == Access::write && t.onGenericWrite) {
+                    t.onGenericWrite();
+                }
+            }
+        }
         backend.setDevice(setIdx);
         launchers.at(setIdx)(streamIdx, dataView);
+    }
+    /* true if running this container changes host-side state that a replayed CUDA graph would not repeat */
+    bool graphSafe() const override { return !writesCachedFields(); }
+    bool writesCachedFields() const
+    {
+        if (!genericBody) {
+            return false;
+        }
+        for (const auto& t : tokens) {
+            if (t.access == Access::write && t.onGenericWrite) {
+                return true;
+            }
+        }
+        return false;
     }
 };
 }  // namespace detail

@@ -105,6 +105,13 @@ class Skeleton
     Skeleton(Skeleton&& o) noexcept { *this = std::move(o); }
     Skeleton& operator=(Skeleton&& o) noexcept
     {
+        if (this == &o) {
+            return *this;
+        }
+        if (mGraphExec) { /* a skeleton that already captured a graph is being re-assigned */
+            cudaGraphExecDestroy(mGraphExec);
+            mGraphExec = nullptr;
+        }
         mBk = o.mBk;
         mHasBk = o.mHasBk;
         mName = std::move(o.mName);
@@ -172,7 +179,14 @@ class Skeleton
 
     void run()
     {
-        const bool graph = mOptions.cudaGraph() && mBk.getDeviceCount() == 1 && mBk.runtime() == Runtime::stream;
+        bool graph = mOptions.cudaGraph() && mBk.getDeviceCount() == 1 && mBk.runtime() == Runtime::stream;
+        for (const auto& n : mNodes) {
+            /* a user lambda that writes a field with an x-face cache invalidates that cache on the HOST at every launch; a
+             * replayed graph would skip it: such sequences are issued launch by launch */
+            if (graph && (n.kind == Node::compute || n.kind == Node::halo) && !n.container.graphSafe()) {
+                graph = false;
+            }
+        }
         if (!graph) {
             NEON_NVTX_PUSH("Skeleton");
             issue();

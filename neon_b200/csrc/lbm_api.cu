@@ -221,6 +221,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
     l.tmapF = nullptr;
     l.groups = (opts >> 18) & 0x3;
     l.numSms = 0;
+    l.exact = ((opts >> 30) & 1) ? 0 : 1;  // NLBM_OPT_REF_LITERAL: the operand-for-operand transcription instead
     const int   kernelSel = peer ? 1 : (opts >> 12) & 0xF;  // 0 auto, 1 direct loads, 2 TMA-fed persistent
     const int   q = (kind == nlbm::kD3Q27_F32 || kind == nlbm::kD3Q27_F64) ? 27 : 19;
     CUtensorMap tmapA, tmapB, tmapF;
@@ -352,6 +353,37 @@ int nlbm_dense_flags_commit(const nlbm_dense_desc* d, void* stream)
         return rc;
     cudaError_t e = nlbm::launchSummary(*d, (cudaStream_t)stream);
     return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flag summary launch");
+}
+
+int nlbm_selftest_exact(int kind, uint64_t n, uint64_t seed, uint64_t* mismatches)
+{
+    if ((kind != 0 && kind != 1) || mismatches == nullptr)
+        return fail(NLBM_ERR_INVALID, "selftest kind %d", kind);
+    unsigned long long* d = nullptr;
+    cudaError_t         e = cudaMalloc(reinterpret_cast<void**>(&d), sizeof(unsigned long long));
+    if (e != cudaSuccess)
+        return cudaFail(e, "selftest alloc");
+    e = cudaMemset(d, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = nlbm::launchSelftestExact(kind, n, seed, d, nullptr);
+    unsigned long long h = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cudaFail(e, "selftest");
+    *mismatches = h;
+    return NLBM_OK;
+}
+
+int nlbm_dense_flags_from_classes(const nlbm_dense_desc* d, const uint8_t* classes, int zm_first, int nplanes, void* stream)
+{
+    if (int rc = checkDesc(d, 4, false, false, true))
+        return rc;
+    if (classes == nullptr || nplanes < 0 || zm_first < 0 || zm_first + nplanes > d->nz_local + 2 * d->z_halo)
+        return fail(NLBM_ERR_INVALID, "classes cover memory planes [%d, %d) of %d", zm_first, zm_first + nplanes, d->nz_local + 2 * d->z_halo);
+    cudaError_t e = nlbm::launchFlagsFromClasses(*d, classes, zm_first, nplanes, (cudaStream_t)stream);
+    return e == cudaSuccess ? NLBM_OK : cudaFail(e, "flags-from-classes launch");
 }
 
 int nlbm_dense_wall_mask(const nlbm_dense_desc* d, int q, int32_t* d_bad, void* stream)
@@ -602,7 +634,8 @@ static int blockStepImpl(nlbm::StepKind kind, const nlbm_block_desc* d, double o
             continue;
         a.firstBlock = r[0];
         a.nBlocks = r[1];
-        cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchBlockStepRef(kind, a, r[1], st) : nlbm::launchBlockStepFast(kind, a, r[1], st);
+        cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchBlockStepRef(kind, a, r[1], st, ((opts >> 30) & 1) == 0)
+                                                      : nlbm::launchBlockStepFast(kind, a, r[1], st);
         if (e != cudaSuccess)
             return cudaFail(e, "block step launch");
     }

@@ -265,8 +265,9 @@ __global__ void __launch_bounds__(BlockCfg<COL, T, VEC>::THREADS, BlockCfg<COL, 
 #pragma unroll
         for (int q = 0; q < Q; ++q)
             p[q] = f[q][i];
-        COL::run(p, omega);
         const bool bulk = flagIsBulk(fl[i]);
+        if (!BulkOnly<COL>::value || bulk)
+            COL::run(p, omega);
 #pragma unroll
         for (int q = 0; q < Q; ++q)
             f[q][i] = bulk ? p[q] : f[q][i];

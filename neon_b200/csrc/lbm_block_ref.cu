@@ -4,10 +4,12 @@
 #include "lbm_host.h"
 
 namespace nlbm {
-cudaError_t launchBlockStepRef(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st)
+cudaError_t launchBlockStepRef(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st, bool exact)
 {
     switch (kind) {
         case kD3Q19_F32:
+            if (exact)  // the same bits with a third of the float<->double conversions (lbm_collide_exact.cuh)
+                return launchBlockStep<CollideD3Q19Exact<0>, float>(a, nBlocks, st);
             return launchBlockStep<CollideD3Q19Ref<float, float, 0>, float>(a, nBlocks, st);
         case kD3Q19_F64:
             return launchBlockStep<CollideD3Q19Ref<double, double, 0>, double>(a, nBlocks, st);

@@ -22,15 +22,18 @@ struct StepLaunch
     const void* tmapF;  // 3-D map over the flag words, box (TX, TY, 1)
     int         groups; // consumer groups of the TMA kernel (0 = default)
     int         numSms;
+    int         exact;  // REFERENCE arithmetic through the conversion-lean evaluation where one exists (same bits)
 };
 cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
 cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
+cudaError_t launchSelftestExact(int kind, unsigned long long n, unsigned long long seed, unsigned long long* dBad, cudaStream_t st);
 // tile width / rows of the TMA kernel for a population of elemBytes and a row of nx cells
 void tmaTileShape(int elemBytes, int nx, int* tx, int* ty);
 
 // lbm_setup.cu
 cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st);
 cudaError_t launchWallCacheBuild(const nlbm_dense_desc& d, int q, int elemBytes, cudaStream_t st);
+cudaError_t launchFlagsFromClasses(const nlbm_dense_desc& d, const uint8_t* cls, int zmFirst, int nPlanes, cudaStream_t st);
 cudaError_t launchClassify(const nlbm_dense_desc& d, int geom, const double* sphere, cudaStream_t st);
 cudaError_t launchWallMask(const nlbm_dense_desc& d, int q, int32_t* d_bad, cudaStream_t st);
 template <typename S>
@@ -40,7 +43,7 @@ cudaError_t launchRhoU(const nlbm_dense_desc& d, void* rho, void* u, cudaStream_
 
 // lbm_block_ref.cu / lbm_block_fast.cu
 struct BlockArgs;
-cudaError_t launchBlockStepRef(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st);
+cudaError_t launchBlockStepRef(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st, bool exact = false);
 cudaError_t launchBlockStepFast(StepKind kind, const BlockArgs& a, uint32_t nBlocks, cudaStream_t st);
 cudaError_t launchBlockClassify(const nlbm_block_desc& d, int geom, const double* sphere, const uint32_t* activeMask, cudaStream_t st);
 cudaError_t launchBlockWallMask(const nlbm_block_desc& d, int q, int32_t* bad, cudaStream_t st);

@@ -88,7 +88,12 @@ __global__ void k_wall_mask(const GeomArgs g, int32_t* __restrict__ bad)
                 m |= 1u << q;
         }
     }
-    g.flags[o] = (cls << NLBM_FLAG_CLASS_SHIFT) | m;
+    // In place (RunCavityTwoPop.cu:239 runs it on (flag, flag)): other threads read THIS word's class bits while the mask
+    // bits change.  Only the mask bits are touched, by atomic read-modify-writes, so the class bits (and any bit of the
+    // word the caller uses for itself) are never rewritten and a concurrent reader always sees them whole.
+    atomicAnd(&g.flags[o], ~kMaskBits);
+    if (m)
+        atomicOr(&g.flags[o], m);
     if (nbad && bad)
         atomicAdd(bad, nbad);
 }
@@ -283,6 +288,32 @@ cudaError_t launchSummary(const nlbm_dense_desc& d, cudaStream_t st)
     k_summary<<<(unsigned)blocks, threads, 0, st>>>(d.flags, const_cast<uint2*>(summaryPtr(d)), const_cast<uint8_t*>(cellMapPtr(d)), d.nx,
                                                     d.ny, nzm, (int)d.pitch_y, d.pitch_z, wpr);
     return cudaGetLastError();
+}
+
+// flag words from one byte per cell (FlagField::setClasses with a host mirror of classes): class bits set, wall bits
+// cleared; padding cells and memory planes the caller has no classes for become `undefined`
+__global__ void k_flags_from_classes(uint32_t* __restrict__ flags, const uint8_t* __restrict__ cls, int nx, int ny, int pitch_y,
+                                     int64_t pitch_z, int zmFirst, int nPlanes)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, zm = blockIdx.z;
+    if (x >= pitch_y)
+        return;
+    uint32_t  c = NLBM_UNDEFINED;
+    const int p = zm - zmFirst;
+    if (x < nx && p >= 0 && p < nPlanes)
+        c = cls[((int64_t)p * ny + y) * nx + x] & 3u;
+    flags[(int64_t)zm * pitch_z + (int64_t)y * pitch_y + x] = c << NLBM_FLAG_CLASS_SHIFT;
+}
+
+cudaError_t launchFlagsFromClasses(const nlbm_dense_desc& d, const uint8_t* cls, int zmFirst, int nPlanes, cudaStream_t st)
+{
+    const int nzm = d.nz_local + 2 * d.z_halo;
+    dim3      block(128), grid(((int)d.pitch_y + 127) / 128, d.ny, nzm);
+    k_flags_from_classes<<<grid, block, 0, st>>>(const_cast<uint32_t*>(d.flags), cls, d.nx, d.ny, (int)d.pitch_y, d.pitch_z, zmFirst, nPlanes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    return launchSummary(d, st);
 }
 
 cudaError_t launchClassify(const nlbm_dense_desc& d, int geom, const double* sphere, cudaStream_t st)

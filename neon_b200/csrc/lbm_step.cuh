@@ -17,8 +17,10 @@
 //    per-cell fix-up executed only by cells whose wallNghBitflag is non-zero.
 //  * results leave through 16-byte streaming stores; non-bulk cells are never written (LbmTools.h:304).
 #pragma once
+#include <type_traits>
 #include <utility>
 
+#include "lbm_collide_exact.cuh"
 #include "lbm_common.cuh"
 
 namespace nlbm {
@@ -67,6 +69,50 @@ struct CollideD3Q19Ref
         const C o9 = (1. - omega) * (C)p[9] + omega * eq9;
         p[9] = (S)o9;
     }
+};
+
+// D3Q19 fp32, the reference's bits at a fraction of the conversions (lbm_collide_exact.cuh): the fast evaluation where its
+// guard holds (positive populations, |u| < 0.1), else the plain one — out of line, it is rare and would double the code.
+static __device__ __noinline__ void collideD3Q19ExactSlow(float* p, const float omega)
+{
+    float f[19];
+#pragma unroll
+    for (int q = 0; q < 19; ++q)
+        f[q] = p[q];
+    exact::collideD3Q19<0>(f, omega);
+#pragma unroll
+    for (int q = 0; q < 19; ++q)
+        p[q] = f[q];
+}
+template <int FMAD>
+struct CollideD3Q19Exact
+{
+    static constexpr int  Q = 19;
+    static constexpr bool kBulkOnly = true;  // skip cells whose result is discarded (their zeros would fail the guard)
+    using Compute = float;
+    __device__ __forceinline__ static void run(float (&p)[19], const float omega)
+    {
+        if (!exact::collideD3Q19<1>(p, omega)) {
+            float t[19];
+#pragma unroll
+            for (int q = 0; q < 19; ++q)
+                t[q] = p[q];
+            collideD3Q19ExactSlow(t, omega);
+#pragma unroll
+            for (int q = 0; q < 19; ++q)
+                p[q] = t[q];
+        }
+    }
+};
+template <class COL, typename = void>
+struct BulkOnly
+{
+    static constexpr bool value = false;
+};
+template <class COL>
+struct BulkOnly<COL, std::enable_if_t<COL::kBulkOnly>>
+{
+    static constexpr bool value = true;
 };
 
 // D3Q19, storage-precision arithmetic with fused multiply-add (agrees with the reference within the
@@ -466,8 +512,9 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
 #pragma unroll
         for (int q = 0; q < Q; ++q)
             p[q] = f[q][i];
-        COL::run(p, omega);
         const bool bulk = flagIsBulk(fl[i]);
+        if (!BulkOnly<COL>::value || bulk)
+            COL::run(p, omega);
 #pragma unroll
         for (int q = 0; q < Q; ++q)
             f[q][i] = bulk ? p[q] : f[q][i];

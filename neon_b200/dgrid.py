@@ -68,6 +68,14 @@ def _aligned_zeros(n: int, dtype: torch.dtype, device: torch.device, align: int 
     return raw[off:off + n]
 
 
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class dGrid:
     kind = "dense"
 
@@ -199,6 +207,19 @@ class dField(_FieldBase):
             self.view4[:, zm0:zm0 + n, :, :nx].copy_(src, non_blocking=True)
         self.commitWalls(stream_idx)
 
+    def copyFrom(self, other: "dField", stream_idx: int = 0) -> None:
+        """Device-to-device copy of another field of the same grid and shape (ghost planes and x-face cache included):
+        the second population field of the two-field scheme starts as a copy of the first, so a host mirror has to
+        cross the bus only once."""
+        assert other.grid is self.grid and other.cardinality == self.cardinality and other.dtype == self.dtype
+        with torch.cuda.stream(self.grid.backend.stream(stream_idx)) if self.grid.backend.runtime == Runtime.stream else _nullctx():
+            self.data.copy_(other.data, non_blocking=True)
+            if self._wall_cache is not None and other._walls_committed:
+                self._wall_cache.copy_(other._wall_cache, non_blocking=True)
+                self._walls_committed = True
+            else:
+                self.commitWalls(stream_idx)
+
     def updateHostDataInto(self, host: torch.Tensor) -> None:
         """Asynchronous device -> host copy of the local slab into ``host`` (pinned, [cardinality, nz_local, ny, nx])."""
         g = self.grid
@@ -248,20 +269,31 @@ class FlagField(_FieldBase):
     def _d(self) -> capi.DenseDesc:
         return self.grid.desc(None, None, self)
 
-    def setClasses(self, cls_global: np.ndarray, stream_idx: int = 0, host_z0: int = 0) -> None:
-        """Upload cell classes [nz, ny, nx] (0 bounceBack, 1 movingWall, 2 bulk); padding and planes outside the box
-        become ``undefined``; wall bits are cleared.  ``host_z0``: global z of the first plane of ``cls_global`` when
-        the caller holds only the planes this rank needs (slab + in-box ghost planes)."""
+    def setClasses(self, cls_global, stream_idx: int = 0, host_z0: int = 0) -> None:
+        """Upload cell classes [nz, ny, nx] (0 bounceBack, 1 movingWall, 2 bulk; any integer numpy array, or a pinned
+        uint8 torch tensor for an asynchronous copy); padding and planes outside the box become ``undefined``; wall
+        bits are cleared.  ``host_z0``: global z of the first plane of ``cls_global`` when the caller holds only the
+        planes this rank needs (slab + in-box ghost planes).  One byte per cell crosses the bus; the flag words are
+        made on the device (nlbm_dense_flags_from_classes)."""
         g = self.grid
         nx, ny, nz = g.dim
-        assert cls_global.shape[1:] == (ny, nx) and host_z0 + cls_global.shape[0] <= nz, cls_global.shape
-        host = np.full((g.nzm, ny, self.pitch_y), capi.UNDEFINED << capi.FLAG_CLASS_SHIFT, np.uint32)
+        assert tuple(cls_global.shape[1:]) == (ny, nx) and host_z0 + cls_global.shape[0] <= nz, cls_global.shape
         planes = self._global_planes()  # consecutive memory planes <-> consecutive global planes
         (zm0, gz0), n = planes[0], len(planes)
-        np.left_shift(cls_global[gz0 - host_z0:gz0 - host_z0 + n], capi.FLAG_CLASS_SHIFT, out=host[zm0:zm0 + n, :, :nx], casting="unsafe")
-        self.cells.copy_(torch.from_numpy(host.view(np.int32)))
-        if g.backend.runtime == Runtime.stream:
-            capi.call("nlbm_dense_flags_commit", C.byref(self._d()), g.backend.streamHandle(stream_idx))
+        part = cls_global[gz0 - host_z0:gz0 - host_z0 + n]
+        if g.backend.runtime != Runtime.stream:  # host-logic runtime: flag words written directly
+            host = np.full((g.nzm, ny, self.pitch_y), capi.UNDEFINED << capi.FLAG_CLASS_SHIFT, np.uint32)
+            np.left_shift(np.asarray(part), capi.FLAG_CLASS_SHIFT, out=host[zm0:zm0 + n, :, :nx], casting="unsafe")
+            self.cells.copy_(torch.from_numpy(host.view(np.int32)))
+            return
+        if isinstance(part, np.ndarray):
+            part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.uint8))
+        assert part.dtype == torch.uint8
+        bk = g.backend
+        with torch.cuda.stream(bk.stream(stream_idx)):
+            dev = part.to(bk.device, non_blocking=True)
+            capi.call("nlbm_dense_flags_from_classes", C.byref(self._d()), dev.data_ptr(), zm0, n, bk.streamHandle(stream_idx))
+            dev.record_stream(bk.stream(stream_idx))
 
     def classify(self, geom: int, sphere: Optional[Sequence[float]] = None, stream_idx: int = 0) -> None:
         """Device-side geometry (RunCavityTwoPop.cu:208-224; SURVEY.md §8d for the sphere cases)."""

@@ -127,7 +127,7 @@ def _cluttered_cavity(oracle, dim, seed, density=0.08):
     return cls
 
 
-VARIANTS = [0, "OPT_FLAG_WORDS", "OPT_FLAGS_SUMMARY_FIRST", "OPT_NO_XFACE_FIXUP_PREFETCH", "OPT_NO_XFACE_PREFETCH",
+VARIANTS = [0, "OPT_REF_LITERAL", "OPT_FLAG_WORDS", "OPT_FLAGS_SUMMARY_FIRST", "OPT_NO_XFACE_FIXUP_PREFETCH", "OPT_NO_XFACE_PREFETCH",
             ("OPT_FLAG_WORDS", "OPT_NO_XFACE_FIXUP_PREFETCH", "OPT_NO_XFACE_PREFETCH")]
 
 
@@ -156,6 +156,49 @@ def test_kernel_variants_agree_bit_for_bit(nb, bk, oracle, q, store, dim):
             out, flag = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, opts=opts)
             assert np.array_equal(flag.masks(), mask)
             assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), f"geom {geom} variant {var}"
+
+
+def test_exact_building_blocks(nb):
+    """The two pieces of the conversion-lean REFERENCE evaluation that are not plain IEEE operations, checked on the device
+    against the instructions they replace: float -> double through an integer multiply-add for every positive normal float
+    (2^31 - 2^24 bit patterns), and the shared-reciprocal division on 3 x 2^30 random quotients inside its guard."""
+    import ctypes as C
+    from neon_b200 import _capi as capi
+    bad = C.c_uint64(123)
+    capi.call("nlbm_selftest_exact", 0, 0, 0, C.byref(bad))
+    assert bad.value == 0, f"{bad.value} floats widen differently"
+    for seed in (1, 2):
+        capi.call("nlbm_selftest_exact", 1, 1 << 29, seed, C.byref(bad))
+        assert bad.value == 0, f"{bad.value} quotients differ from IEEE division"
+
+
+@pytest.mark.parametrize("ulb", [0.2, 0.45])
+def test_reference_bits_outside_the_guard_of_the_lean_evaluation(nb, bk, oracle, ulb):
+    """REFERENCE arithmetic for D3Q19 fp32 runs the conversion-lean evaluation (csrc/lbm_collide_exact.cuh) where its guard
+    holds (positive populations, |u| < 0.1) and the plain one elsewhere, cell by cell.  A lid far faster than any valid
+    simulation (Mach > 0.3, negative populations next to the lid) makes both paths run inside the same warps: the bits
+    must still be the oracle's, on dGrid with both kernels and on bGrid."""
+    from neon_b200 import problems as P
+    dim = (72, 24, 16)
+    cls = oracle.classify(1, *dim)
+    mask = oracle.wall_mask(19, cls)
+    pop = oracle.init_pop(19, cls, np.float32, ulb)
+    assert np.array_equal(pop, P.host_populations(19, cls, np.float32, ulb))
+    omega, iters = 1.1, 8
+    ref = oracle.run(19, pop, cls, mask, omega, iters)
+    assert np.isfinite(ref).all()
+    rho_u = oracle.rho_u(ref, cls, mask)
+    assert np.abs(rho_u[1][:, cls == oracle.BULK]).max() > 0.12, "the case must leave the guard"
+    for opts in (nb.opt_kernel(nb.KERNEL_DIRECT), nb.opt_kernel(nb.KERNEL_TMA), nb.opt_kernel(nb.KERNEL_DIRECT) | nb.OPT_REF_LITERAL):
+        out, _ = run_cuda(nb, bk, 19, np.float32, cls, pop, omega, iters, nb.ARITH_REFERENCE, opts=opts)
+        assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), hex(opts)
+    grid = nb.bGrid(bk, dim)
+    pop0, pop1, flag = P.setup_host(grid, 19, np.float32, cls, pop)
+    it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, arith=nb.ARITH_REFERENCE)
+    for _ in range(iters):
+        it.run()
+    bk.syncAll()
+    assert np.array_equal(it.getInput().updateHostData().view(np.uint8), ref.view(np.uint8))
 
 
 def test_device_setup_matches_oracle(nb, bk, oracle):

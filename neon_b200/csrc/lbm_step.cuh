@@ -136,8 +136,55 @@ struct CollideD3Q19Fast
         else
             return __fma_rn(a, b, c);
     }
+    // fp32: float arithmetic only, but with the reference's ROUNDING POINTS.  In the reference (ComputeFP = float) the moments,
+    // usqr and cu are float operations — repeated here operation for operation (the three divisions through the shared
+    // reciprocal of lbm_collide_exact.cuh) — eq and eqopp are double expressions rounded to float, omega*eq is a float product
+    // and the relaxation a double sum rounded to float.  Here rho*w is carried as two floats, so eq = rh + (rh*s + rl) is
+    // within ~0.6 ulp of the correctly rounded value; eqopp, omega*eq and the relaxation (one FMA: both products exact)
+    // then round as the reference's.  Measured on the CPU model of this arithmetic (tools/arith_model.c, variant 12): 0.1 %
+    // of the stored values differ from the reference per iteration, by one ulp, against 6-30 % for the round-1 FAST
+    // (variant 4), and the long-run error stays below 4.5e-6 at 128^3 x 300 iterations where that one reached 1.1e-5.
+    __device__ __forceinline__ static void runF32(float (&p)[19], const float omega)
+    {
+        using namespace exact;
+        const float X_M1 = fadd(fadd(fadd(fadd(p[0], p[3]), p[4]), p[5]), p[6]);
+        const float X_P1 = fadd(fadd(fadd(fadd(p[10], p[13]), p[14]), p[15]), p[16]);
+        const float X_0 = fadd(fadd(fadd(fadd(fadd(fadd(fadd(fadd(p[9], p[1]), p[2]), p[7]), p[8]), p[11]), p[12]), p[17]), p[18]);
+        const float Y_M1 = fadd(fadd(fadd(fadd(p[1], p[3]), p[7]), p[8]), p[14]);
+        const float Y_P1 = fadd(fadd(fadd(fadd(p[4], p[11]), p[13]), p[17]), p[18]);
+        const float Z_M1 = fadd(fadd(fadd(fadd(p[2], p[5]), p[7]), p[16]), p[18]);
+        const float Z_P1 = fadd(fadd(fadd(fadd(p[6], p[8]), p[12]), p[15]), p[17]);
+        const float rho = fadd(fadd(X_M1, X_P1), X_0);
+        float       u0, u1, u2;
+        div3(fadd(X_P1, -X_M1), fadd(Y_P1, -Y_M1), fadd(Z_P1, -Z_M1), rho, u0, u1, u2);
+        const float nus = -fmul(1.5f, fadd(fadd(fmul(u0, u0), fmul(u1, u1)), fmul(u2, u2)));
+        const float cu[9] = {u0, u1, u2, fadd(u0, u1), fadd(u0, -u1), fadd(u0, u2), fadd(u0, -u2), fadd(u1, u2), fadd(u1, -u2)};
+        const float om1 = fadd(1.f, -omega);
+        // rho * w as hi + lo for w = 1/18, 1/36, 1/3 (w = wh + wl, both floats)
+        constexpr float wh18 = (float)(1. / 18.), wl18 = (float)(1. / 18. - (double)wh18);
+        constexpr float wh36 = (float)(1. / 36.), wl36 = (float)(1. / 36. - (double)wh36);
+        constexpr float wh3 = (float)(1. / 3.), wl3 = (float)(1. / 3. - (double)wh3);
+        const float     rh18 = fmul(rho, wh18), rl18 = __fmaf_rn(rho, wl18, __fmaf_rn(rho, wh18, -rh18));
+        const float     rh36 = fmul(rho, wh36), rl36 = __fmaf_rn(rho, wl36, __fmaf_rn(rho, wh36, -rh36));
+        const float     rh3 = fmul(rho, wh3), rl3 = __fmaf_rn(rho, wl3, __fmaf_rn(rho, wh3, -rh3));
+        const float     rx18 = fmul(rh18, 6.f), rx36 = fmul(rh36, 6.f);
+#pragma unroll
+        for (int g = 0; g < 9; ++g) {
+            const float rh = g < 3 ? rh18 : rh36, rl = g < 3 ? rl18 : rl36, rx = g < 3 ? rx18 : rx36, c = cu[g];
+            const float s = __fmaf_rn(fmul(4.5f, c), c, __fmaf_rn(-3.f, c, nus));  // -3cu + 4.5cu^2 - usqr
+            const float eq = fadd(rh, __fmaf_rn(rh, s, rl));
+            const float eqopp = __fmaf_rn(rx, c, eq);
+            p[g] = __fmaf_rn(om1, p[g], fmul(omega, eq));
+            p[g + 10] = __fmaf_rn(om1, p[g + 10], fmul(omega, eqopp));
+        }
+        p[9] = __fmaf_rn(om1, p[9], fmul(omega, fadd(rh3, __fmaf_rn(rh3, nus, rl3))));
+    }
     __device__ __forceinline__ static void run(T (&p)[19], const T omega)
     {
+        if constexpr (sizeof(T) == 4) {
+            runF32(p, omega);
+            return;
+        }
         const T X_M1 = p[0] + p[3] + p[4] + p[5] + p[6];
         const T X_P1 = p[10] + p[13] + p[14] + p[15] + p[16];
         const T X_0 = p[9] + p[1] + p[2] + p[7] + p[8] + p[11] + p[12] + p[17] + p[18];
@@ -210,10 +257,67 @@ struct CollideD3Q27Fast
 {
     static constexpr int Q = 27;
     using Compute = T;
+    // fp32: as CollideD3Q19Fast::runF32 — float arithmetic with the reference's rounding points.  With T = float the reference
+    // (collide.h:311-334, util.h:47-62) computes rho, vel, usqr and cu in float (repeated here operation for operation; a
+    // product by a lattice velocity component is exact), feq in double (double weights and literals) rounded to float — here
+    // rho*w carried as two floats — and the relaxation in float without contraction.  CPU model (tools/arith_model.c,
+    // variant 13): 3.3e-6 after 100 iterations at 64^3 where the FMA-everywhere version reached 1.4e-5.
+    __device__ __forceinline__ static void runF32(float (&f)[27], const float omega)
+    {
+        using namespace exact;
+        using L = Lattice<27>;
+        float rho = 0.f, m[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 27; ++q)
+            rho = fadd(rho, f[q]);
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (L::c(q, d) == 1)
+                    m[d] = fadd(m[d], f[q]);
+                else if (L::c(q, d) == -1)
+                    m[d] = fadd(m[d], -f[q]);
+            }
+        }
+        float u[3];
+        div3(m[0], m[1], m[2], rho, u[0], u[1], u[2]);
+        const float nus = -fmul(1.5f, fadd(fadd(fmul(u[0], u[0]), fmul(u[1], u[1])), fmul(u[2], u[2])));
+        const float om1 = fadd(1.f, -omega);
+        // rho * w as hi + lo for the four weight classes
+        float rh[4], rl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double wd = k == 0 ? 8.0 / 27.0 : (k == 1 ? 2.0 / 27.0 : (k == 2 ? 1.0 / 54.0 : 1.0 / 216.0));
+            const float  wh = (float)wd, wl = (float)(wd - (double)wh);
+            rh[k] = fmul(rho, wh);
+            rl[k] = __fmaf_rn(rho, wl, __fmaf_rn(rho, wh, -rh[k]));
+        }
+#pragma unroll
+        for (int q = 0; q < 27; ++q) {
+            float cu = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (L::c(q, d) == 1)
+                    cu = fadd(cu, u[d]);
+                else if (L::c(q, d) == -1)
+                    cu = fadd(cu, -u[d]);
+            }
+            cu = fmul(cu, 3.f);
+            const int   k = (L::c(q, 0) != 0) + (L::c(q, 1) != 0) + (L::c(q, 2) != 0);
+            const float s = __fmaf_rn(fmul(0.5f, cu), cu, fadd(cu, nus));  // cu + cu^2/2 - usqr
+            const float feq = fadd(rh[k], __fmaf_rn(rh[k], s, rl[k]));
+            f[q] = fadd(fmul(om1, f[q]), fmul(omega, feq));
+        }
+    }
     __device__ __forceinline__ static void run(T (&f)[27], const T omega)
     {
         using L = Lattice<27>;
         using F = CollideD3Q19Fast<T, FMAD>;
+        if constexpr (sizeof(T) == 4) {
+            runF32(f, omega);
+            return;
+        }
         T rho = 0, m[3] = {0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 27; ++q) {

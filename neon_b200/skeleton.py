@@ -147,6 +147,31 @@ class Skeleton:
             else:
                 n.container.run(n.stream, n.view)
 
+    def timeline(self):
+        """One run() with a CUDA event in front of and behind every node (on the node's stream): returns
+        [(stream, kind, name, view, start_ms, end_ms)] relative to the first node's start — the device-side picture nsys
+        would draw of one iteration (which node overlapped which), measured without a profiler.  The extra events
+        serialise nothing: they are recorded on the streams the nodes already use."""
+        bk = self.backend
+        assert bk.runtime == Runtime.stream
+        marks = []
+        base = torch.cuda.Event(enable_timing=True)
+        base.record(bk.stream(0))
+        for s in range(1, len(bk._streams)):
+            bk.stream(s).wait_event(base)
+        saved = self.nodes
+        for n in saved:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(bk.stream(n.stream))
+            self.nodes = [n]
+            self._issue()
+            e1.record(bk.stream(n.stream))
+            marks.append((n, e0, e1))
+        self.nodes = saved
+        bk.syncAll()
+        return [(n.stream, n.kind, n.name, n.view.name if n.view else None, base.elapsed_time(e0), base.elapsed_time(e1))
+                for n, e0, e1 in marks]
+
     def run(self) -> None:
         if not self._use_graph:
             self._issue()

@@ -52,6 +52,8 @@ struct Args
     bool        isDouble = false;
     std::string grid = "dGrid";
     std::string dump;
+    bool        occ = false;      // --occ standard: the reference's Skeleton splits INTERNAL / BOUNDARY (Occ::standard)
+    bool        sameGpu = false;  // --same-gpu: every partition on device 0 (oversubscribed device list, as the reference's tests do)
     std::string device = "cpu";  // "gpu": the reference's own CUDA backend (Neon::Runtime::stream), devices 0..nDev-1
     double      Re = 100., ulb = 0.04;
 };
@@ -80,7 +82,7 @@ static int runCase(const Args& a)
     const bool       onGpu = a.device == "gpu";
     if (onGpu) {
         for (int i = 0; i < a.nDev; ++i)
-            devs[i] = i;
+            devs[i] = a.sameGpu ? 0 : i;
     }
     Neon::Backend bk(devs, onGpu ? Neon::Runtime::stream : Neon::Runtime::openmp);
     Lattice          lattice(bk);
@@ -100,7 +102,7 @@ static int runCase(const Args& a)
     const FP     omega = static_cast<FP>(omegaD);
 
     LbmIterationD3Q19<PopulationField, FP> iteration(Neon::set::StencilSemantic::standard,
-                                                     Neon::skeleton::Occ::none,
+                                                     a.occ ? Neon::skeleton::Occ::standard : Neon::skeleton::Occ::none,
                                                      Neon::set::TransferMode::get,
                                                      pop0, pop1, flag, omega);
 
@@ -240,6 +242,10 @@ int main(int argc, char** argv)
             a.dump = next();
         } else if (k == "--device") {
             a.device = next();
+        } else if (k == "--occ") {
+            a.occ = std::string(next()) == "standard";
+        } else if (k == "--same-gpu") {
+            a.sameGpu = true;
         } else {
             std::fprintf(stderr, "unknown arg %s\n", k.c_str());
             return 1;

@@ -192,6 +192,43 @@ static void collide19(int variant, const float* p, float omega, float* out)
         }
         const float eq9 = rho * (1. / 3.) * (1. - usqr);
         out[9] = (1. - omega) * p[9] + omega * eq9;
+    } else if (variant == 11) {
+        /* float only, but with the reference's rounding points: eq and eqopp rounded to float on their own, omega*eq a float
+         * product, the relaxation one FMA (== the reference's double sum rounded to float, double rounding aside) */
+        const float om1 = 1.f - omega;
+        const float rw18 = rho * (float)(1. / 18.), rw36 = rho * (float)(1. / 36.);
+        const float nus = -usqr;
+        for (int g = 0; g < 9; ++g) {
+            const float rw = g < 3 ? rw18 : rw36, c = cu[g];
+            const float s = fmaf(4.5f * c, c, fmaf(-3.f, c, nus)); /* -3c + 4.5c^2 - usqr */
+            const float eq = fmaf(rw, s, rw);
+            const float eqopp = fmaf(rw * 6.f, c, eq);
+            out[g] = fmaf(om1, p[g], omega * eq);
+            out[g + 10] = fmaf(om1, p[g + 10], omega * eqopp);
+        }
+        const float r3 = rho * (float)(1. / 3.);
+        out[9] = fmaf(om1, p[9], omega * fmaf(r3, nus, r3));
+    } else if (variant == 12) {
+        /* as 11 with rho*w carried as two floats (hi + lo): eq is then within ~0.6 ulp of the reference's */
+        const float om1 = 1.f - omega;
+        const float nus = -usqr;
+        float rh[3], rl[3];
+        const double wd[3] = {1. / 18., 1. / 36., 1. / 3.};
+        for (int k = 0; k < 3; ++k) {
+            const float wh = (float)wd[k], wl = (float)(wd[k] - (double)wh);
+            rh[k] = rho * wh;
+            rl[k] = fmaf(rho, wh, -rh[k]) + rho * wl;
+        }
+        for (int g = 0; g < 9; ++g) {
+            const int   k = g < 3 ? 0 : 1;
+            const float c = cu[g];
+            const float s = fmaf(4.5f * c, c, fmaf(-3.f, c, nus));
+            const float eq = rh[k] + fmaf(rh[k], s, rl[k]);
+            const float eqopp = fmaf(rh[k] * 6.f, c, eq);
+            out[g] = fmaf(om1, p[g], omega * eq);
+            out[g + 10] = fmaf(om1, p[g + 10], omega * eqopp);
+        }
+        out[9] = fmaf(om1, p[9], omega * (rh[2] + fmaf(rh[2], nus, rl[2])));
     } else if (variant == 8) {
         /* float-float where it matters: eq, eqopp rounded (almost always) as the reference rounds them, the relaxation
          * as one FMA plus the product's error term */
@@ -217,19 +254,46 @@ static void collide19(int variant, const float* p, float omega, float* out)
             const float c6 = 6.f * c, c6l = fmaf(6.f, c, -c6);
             const float m = rh * c6, ml = fmaf(rh, c6, -m) + fmaf(rl, c6, rh * c6l);
             const float eqopp = eq + (m + ml);  /* one rounding of eq + m (+ml): approx */
-            const float h = omega * eq, l = fmaf(omega, eq, -h);
-            out[g] = fmaf(om1, p[g], h) + l;
-            const float h2 = omega * eqopp, l2 = fmaf(omega, eqopp, -h2);
-            out[g + 10] = fmaf(om1, p[g + 10], h2) + l2;
+            out[g] = fmaf(om1, p[g], omega * eq);
+            out[g + 10] = fmaf(om1, p[g + 10], omega * eqopp);
         }
         {
             const double wd = 1. / 3.;
             const float  wh = (float)wd, wl = (float)(wd - (double)wh);
             const float  rh = rho * wh, rl = fmaf(rho, wh, -rh) + rho * wl;
             const float  eq9 = rh + fmaf(rh, -usqr, rl);
-            const float  h = omega * eq9, l = fmaf(omega, eq9, -h);
-            out[9] = fmaf(om1, p[9], h) + l;
+            out[9] = fmaf(om1, p[9], omega * eq9);
         }
+    }
+}
+
+/* D3Q27 fp32 storage, float only with the reference's rounding points (collide.h:311-334, util.h:47-62 with T = float):
+ * rho, vel, usqr, cu are float arithmetic there and are repeated operation for operation; feq is evaluated in double there
+ * (double weights and literals) and rounded to float: here rho*w is carried as two floats; the relaxation is float
+ * arithmetic without contraction, as the reference's. */
+static void collide27_v13(const int (*c)[3], const double* w, const float* f, float omega, float* out)
+{
+    float rho = 0;
+    for (int q = 0; q < 27; ++q)
+        rho += f[q];
+    float vel[3] = {0, 0, 0};
+    for (int q = 0; q < 27; ++q)
+        for (int d = 0; d < 3; ++d)
+            vel[d] += f[q] * (float)c[q][d];
+    for (int d = 0; d < 3; ++d)
+        vel[d] /= rho;
+    const float usqr = 1.5f * (vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+    const float om1 = 1 - omega;
+    for (int q = 0; q < 27; ++q) {
+        float cu = 0;
+        for (int d = 0; d < 3; ++d)
+            cu += (float)c[q][d] * vel[d];
+        cu *= 3.0f;
+        const float wh = (float)w[q], wl = (float)(w[q] - (double)wh);
+        const float rh = rho * wh, rl = fmaf(rho, wh, -rh) + rho * wl;
+        const float s = fmaf(0.5f * cu, cu, cu - usqr);
+        const float feq = rh + fmaf(rh, s, rl);
+        out[q] = om1 * f[q] + omega * feq;
     }
 }
 
@@ -263,7 +327,9 @@ void model_step(int variant, int isd, int Q, const int* c_, const int* opp, cons
                     float f[27], out[27];
                     for (int q = 0; q < Q; ++q)
                         f[q] = (float)in[q];
-                    if (variant >= 4 && Q == 19)
+                    if (variant == 13 && Q == 27)
+                        collide27_v13(c, w, f, (float)omega, out);
+                    else if (variant >= 4 && Q == 19)
                         collide19(variant, f, (float)omega, out);
                     else if (variant == 1)
                         collide1_f32(Q, c, w, f, (float)omega, out);

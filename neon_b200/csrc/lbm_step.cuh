@@ -851,10 +851,13 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     a.lprLog2 = lprLog2;
     const int rpw = 32 >> lprLog2;
     const int segs = (a.nx + (VEC << lprLog2) - 1) / (VEC << lprLog2);
-    // the 8 warps of a block stack in y by default, so that the warps which need the extra round trip of wall handling
-    // (segments touching an x wall) share blocks and do not hold back plain ones
+    // Block shape: sx warps side by side in x, rows of them stacked in y.  D3Q19 fp32 (16-byte accesses): 4 x 2 — a block then
+    // reads, per population, two contiguous 2 KB stretches instead of eight of 512 bytes, which the DRAM pages like better
+    // (measured on B200, profiles/r02f_rows_sweep.log: 512^3 42.28 -> 43.24 GLUPS, 1024x1024x128 42.74 -> 43.16, 256^3 39.2 ->
+    // 41.4, 128^3 30.0 -> 33.7; while the x-wall fix-ups still cost a dependent round trip the stacked shape was the better
+    // one, round 1).  The other lattices / precisions keep the 1 x 8 stack (D3Q27 fp64: 13.93 vs 13.12 GLUPS).
     int warps = kStepThreads / 32;
-    int sx = 1;
+    int sx = (COL::Q == 19 && sizeof(T) == 4 && VEC == 4) ? 4 : 1;
     int rows = warps / sx;
     if (rowsLog2 > 0) {
         rows = 1 << (rowsLog2 - 1);

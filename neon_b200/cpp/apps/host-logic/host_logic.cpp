@@ -134,10 +134,10 @@ int main()
         sk.sequence({it}, "occ", skeleton::Options(skeleton::Occ::standard, set::TransferMode::put));
         CHECK(sk.scheduleToString() ==
               "0 fork fork -\n"
-              "0 compute LBM_iteration_D3Q19 INTERNAL\n"
               "1 halo haloUpdate(pop0,streaming,put) -\n"
               "1 compute LBM_iteration_D3Q19 BOUNDARY\n"
-              "0 join join -\n");
+              "0 compute LBM_iteration_D3Q19 INTERNAL\n"
+              "0 join join -\n");  // the high-priority side stream is issued first
         CHECK(bk.getStreamSetCount() == 2);
         sk.ioToDot("/tmp/neon_b200_host_logic_graph");
         std::ifstream dot("/tmp/neon_b200_host_logic_graph.dot");
@@ -150,6 +150,48 @@ int main()
         skeleton::Skeleton s1(one);
         s1.sequence({Tools::iteration(set::StencilSemantic::streaming, a, f, 1.f, b)}, "single", skeleton::Options(skeleton::Occ::standard, set::TransferMode::get));
         CHECK(s1.scheduleToString() == "0 compute LBM_iteration_D3Q19 STANDARD\n");  // one device: no halo, no split
+    }
+    {
+        // ---- the Skeleton's graph for map -> stencil -> map under every Occ (multiGpuGraph.cpp:120-301): containers whose
+        // body is never run, only their tokens matter here
+        auto fa = grid.newField<float, 19>("fa", 19, 0.f), fb = grid.newField<float, 19>("fb", 19, 0.f);
+        auto fc = grid.newField<float, 19>("fc", 19, 0.f), fd = grid.newField<float, 19>("fd", 19, 0.f);
+        auto mk = [&](const std::string& name, const Pop& in, Pop& out, bool stencil) {
+            return set::Container::factoryDeviceManaged(name, bk, [&](SetIdx, set::Loader& L) {
+                if (stencil) {
+                    L.load(in, Pattern::STENCIL, set::StencilSemantic::standard);
+                } else {
+                    L.load(in);
+                }
+                L.load(out);
+                return [](int, DataView) {};
+            });
+        };
+        std::vector<set::Container> seq = {mk("M1", fa, fb, false), mk("S", fb, fc, true), mk("M2", fc, fd, false)};
+        skeleton::Skeleton          sk(bk);
+        sk.sequence(seq, "std", skeleton::Options(skeleton::Occ::standard, set::TransferMode::get));
+        CHECK(sk.dependenciesToString() ==
+              "compute M1 STANDARD <-\n"
+              "halo haloUpdate(fb,grid,get) - <- [compute M1 STANDARD]\n"
+              "compute S BOUNDARY <- [halo haloUpdate(fb,grid,get) -]\n"
+              "compute S INTERNAL <- [compute M1 STANDARD]\n"
+              "compute M2 STANDARD <- [compute S BOUNDARY] [compute S INTERNAL]\n");
+        sk.sequence(seq, "ext", skeleton::Options(skeleton::Occ::extended, set::TransferMode::get));
+        const std::string ext = sk.dependenciesToString();
+        CHECK(ext.find("halo haloUpdate(fb,grid,get) - <- [compute M1 BOUNDARY]\n") != std::string::npos);  // overlaps M1's INTERNAL half
+        CHECK(ext.find("compute S INTERNAL <- [compute M1 BOUNDARY] [compute M1 INTERNAL]\n") != std::string::npos);
+        CHECK(ext.find("compute M2 STANDARD") != std::string::npos);
+        CHECK(sk.scheduleToString().find("compute M1 BOUNDARY") < sk.scheduleToString().find("compute M1 INTERNAL"));
+        sk.sequence(seq, "two", skeleton::Options(skeleton::Occ::twoWayExtended, set::TransferMode::get));
+        const std::string two = sk.dependenciesToString();
+        CHECK(two.find("compute M2 INTERNAL <- [compute S INTERNAL]\n") != std::string::npos);
+        CHECK(two.find("compute M2 BOUNDARY <- [compute S BOUNDARY]\n") != std::string::npos);
+        sk.sequence(seq, "none", skeleton::Options(skeleton::Occ::none, set::TransferMode::get));
+        CHECK(sk.scheduleToString() ==
+              "0 compute M1 STANDARD\n"
+              "0 halo haloUpdate(fb,grid,get) -\n"
+              "0 compute S STANDARD\n"
+              "0 compute M2 STANDARD\n");
     }
     {
         auto halo = pop0.newHaloUpdate(set::StencilSemantic::streaming, set::TransferMode::get);

@@ -67,7 +67,9 @@ def parse():
                          "speculative x-face fix-up operands, 1<<30 literal transcription in REFERENCE arithmetic); never changes results")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: halo update in front of the consumer instead of pushed after BOUNDARY")
     ap.add_argument("--graph-iters", type=int, default=-1,
-                    help="one device: iterations per CUDA-graph replay (0 = plain launches; default: 0 for boxes above 2^24 cells, else 10)")
+                    help="one device: iterations per host call — one multi-iteration launch, or a CUDA-graph replay with --no-persistent "
+                         "(0 = plain launches; default: 0 for boxes above 2^22 cells, else 10)")
+    ap.add_argument("--no-persistent", action="store_true", help="small boxes: CUDA-graph replay of single-iteration launches instead of the multi-iteration kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline line only: no arith_reference, no extra_configs")
@@ -95,6 +97,10 @@ def workload(name: str, n: int):
         return dict(key=name, name=f"flow over sphere D3Q19 fp32 1024x512x512 bGrid (8^3 blocks, bounce-back), z block layers over {n} GPU(s)", q=19,
                     dtype="float32", dim=(1024, 512, 512), scaling="strong", grid="bGrid", geom=2, sphere=(392.0, 277.0, 256.0, 60.0),
                     omega=1.0 / (3.0 * 0.04 * 60.0 / 100.0 + 0.5))
+    if name.startswith("box"):  # box<NX>x<NY>x<NZ>: lid-driven cavity in an arbitrary box (layout experiments)
+        e = [int(v) for v in name[3:].split("x")]
+        return dict(key=name, name=f"lid-driven cavity D3Q19 fp32 {e[0]}x{e[1]}x{e[2]} dGrid", q=19, dtype="float32", dim=tuple(e),
+                    scaling="strong" if n > 1 else "weak")
     if name.startswith("bcavity"):
         e = int(name[len("bcavity"):])
         return dict(key=name, name=f"lid-driven cavity D3Q19 fp32 {e}^3 bGrid (8^3 blocks)", q=19, dtype="float32", dim=(e, e, e),
@@ -326,7 +332,7 @@ class Job:
         # which ~5 us is launch overhead), so G iterations are captured once into a CUDA graph and replayed
         graph_iters = args.graph_iters
         if graph_iters < 0:
-            graph_iters = 10 if (self.world == 1 and cells <= (1 << 24)) else 0
+            graph_iters = 10 if (self.world == 1 and cells <= (1 << 22)) else 0
         if self.world > 1:
             graph_iters = 0
         it = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q,
@@ -334,7 +340,12 @@ class Job:
         main_stream = bk.stream(0)
         per_call = 1
         runner = it.run
-        if graph_iters > 1:
+        if graph_iters > 1 and not is_block and not args.no_persistent:
+            per_call = graph_iters + (graph_iters & 1)  # LbmIteration.runMany: G iterations in one cooperative launch
+
+            def runner():
+                it.runMany(per_call)
+        elif graph_iters > 1:
             per_call = graph_iters + (graph_iters & 1)
             it.runGraph(per_call)  # builds the graph (LbmIteration.runGraph: G iterations per host call)
 
@@ -365,7 +376,7 @@ class Job:
         nnb = (dn is not None) + (up is not None)
         pipelined = self.world > 1 and not args.no_pipeline and args.transport in ("auto", "ipc") and occ != nb.Occ.none
         if self.world == 1:
-            launches_step = 1
+            launches_step = 1.0 / per_call if (graph_iters > 1 and not is_block and not args.no_persistent) else 1
         elif args.transport == "fused":
             launches_step = 1 + nnb  # step+push kernel, one flag wait per neighbour
         elif pipelined:
@@ -405,8 +416,9 @@ class Job:
         res = {"workload": wl["name"], "key": wl["key"], "metric": f"LBM MLUPS (D3Q{q} {'fp32' if dtype.itemsize == 4 else 'fp64'})",
                "value": mlups, "unit": "MLUPS", "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": wl["scaling"],
                "dtype": "f32" if dtype.itemsize == 4 else "f64", "arith": arith_name, "dim": list(dim), "lattice": f"D3Q{q}",
-               "grid": "bGrid" if is_block else "dGrid", "roofline": roofline, "gpu_launches": launches_step * steps,
-               "graph_iters": per_call if graph_iters > 1 else 0, "l2": l2_note, "clocks": clocks,
+               "grid": "bGrid" if is_block else "dGrid", "roofline": roofline, "gpu_launches": int(round(launches_step * steps)),
+               "graph_iters": per_call if graph_iters > 1 else 0,
+               "iterations_per_launch": per_call if (graph_iters > 1 and not is_block and not args.no_persistent) else 1, "l2": l2_note, "clocks": clocks,
                "partition": ((f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes")
                              if self.world > 1 else "single partition")}
         del it, runner
@@ -588,7 +600,7 @@ def main():
                            **({"EXPERIMENT_wrong_results": args.experiment} if args.experiment else {}),
                            "occ": args.occ if job.world > 1 else "n/a (1 partition)",
                            "halo_transport": args.transport if job.world > 1 else "n/a", "l2": head["l2"], "partition": head["partition"],
-                           "graph_iters": head["graph_iters"]},
+                           "graph_iters": head["graph_iters"], "iterations_per_launch": head["iterations_per_launch"]},
                 "roofline": head["roofline"], "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e,
                 "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "arith_reference": arith_ref, "extra_configs": extras}
         print(json.dumps(line), flush=True)

@@ -226,6 +226,17 @@ typedef struct nlbm_peer_desc {
     uint32_t* counters;      /* 2 words of THIS device's memory, zero before the first call, owned by the caller */
     uint32_t  value;
 } nlbm_peer_desc;
+/* ---- several iterations in ONE launch (small boxes) ---------------------------------------------------------------------
+ * `iterations` LBM iterations of a partition WITHOUT neighbours (d->z_halo == 0) in one cooperative launch: iteration t reads
+ * d->pop_in when t is even, else d->pop_out, and writes the other field — the two-field scheme of LbmIteration.h:56-61 without
+ * returning to the host (or to the stream) in between.  The result is in pop_out when `iterations` is odd, else in pop_in.
+ * d->wall_cache is pop_out's x-face cache as in a step call, wall_cache_in the one of pop_in (both may be NULL).  kind as in
+ * nlbm_dense_step_push (0 d3q19_f32 ... 4 d3q27_f64).  A box of a few hundred thousand cells iterates in ~10 us as a kernel of its
+ * own — launch, ramp-up and tail cost as much as the work; here one resident grid walks the tiles and meets at a grid-wide
+ * barrier between iterations, and while both fields fit the L2 the populations never leave the chip.  Same results as
+ * `iterations` step calls, bit for bit.                                                                                    */
+int nlbm_dense_step_n(int kind, const nlbm_dense_desc* d, const void* wall_cache_in, double omega, int iterations, int opts, void* stream);
+
 int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream);
 
 /* LbmContainers::computeRhoAndU, LbmTools.h:384-437 (D3Q19).  rho: [zm][y][x] with the

@@ -116,6 +116,7 @@ _SIGNATURES = {
     "nlbm_d3q19_f32c64_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
     "nlbm_d3q27_f32_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
     "nlbm_d3q27_f64_dense_step": (C.c_int, [_D, C.c_double, C.c_int, C.c_int, _P]),
+    "nlbm_dense_step_n": (C.c_int, [C.c_int, _D, _P, C.c_double, C.c_int, C.c_int, _P]),
     "nlbm_dense_step_push": (C.c_int, [C.c_int, _D, C.POINTER(PeerDesc), C.c_double, C.c_int, _P]),
     "nlbm_d3q19_f32_dense_rho_u": (C.c_int, [_D, _P, _P, _P]),
     "nlbm_d3q19_f64_dense_rho_u": (C.c_int, [_D, _P, _P, _P]),

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "Neon/Neon.h"
@@ -31,11 +32,19 @@ void report(const char* what, bool ok, double err)
 }
 
 // ---------------------------------------------------------------------------------------------------------- 1. MAP
-void testAxpy(const Neon::Backend& bk, int n)
+template <typename Grid>
+void testAxpy(const Neon::Backend& bk, int n, const char* gridName)
 {
-    using Field = Neon::dGrid::Field<double, 3>;
-    Neon::dGrid grid(bk, {n, n + 3, n + 1}, [](const Neon::index_3d&) { return true; }, Neon::domain::Stencil());
-    Field       x = grid.newField<double, 3>("x", 3, 0.0), y = grid.newField<double, 3>("y", 3, 0.0);
+    using Field = typename Grid::template Field<double, 3>;
+    /* block-sparse grids: only a ball of cells is active, so the active mask decides which threads run the lambda */
+    const bool           sparse = std::is_same_v<Grid, Neon::bGrid>;
+    const Neon::index_3d dim(n, n + 3, std::max(n + 1, 16 * bk.getDeviceCount()));
+    auto                 active = [=](const Neon::index_3d& p) {
+        const double dx = p.x - 0.5 * dim.x, dy = p.y - 0.5 * dim.y, dz = p.z - 0.5 * dim.z;
+        return !sparse || dx * dx + dy * dy + 0.25 * dz * dz < 0.2 * dim.x * dim.x;
+    };
+    Grid grid(bk, dim, active, Neon::domain::Stencil());
+    Field       x = grid.template newField<double, 3>("x", 3, 0.0), y = grid.template newField<double, 3>("y", 3, 0.0);
     x.forEachActiveCell([](const Neon::index_3d& p, const int& c, double& v) { v = 0.25 * p.x - 0.5 * p.y + p.z + c; });
     y.forEachActiveCell([](const Neon::index_3d& p, const int& c, double& v) { v = 1.0 + p.x * p.y - c * p.z; });
     x.updateDeviceData();
@@ -44,7 +53,7 @@ void testAxpy(const Neon::Backend& bk, int n)
     auto         axpy = grid.newContainer("axpy", [&](Neon::set::Loader& L) {
         const auto& xp = L.load(const_cast<const Field&>(x));
         auto&       yp = L.load(y);
-        return [=] NEON_CUDA_HOST_DEVICE(const Neon::dGrid::Idx& i) mutable {
+        return [=] NEON_CUDA_HOST_DEVICE(const typename Grid::Idx& i) mutable {
             for (int c = 0; c < yp.cardinality(); ++c) {
                 yp(i, c) = yp(i, c) + a * xp(i, c);
             }
@@ -60,7 +69,10 @@ void testAxpy(const Neon::Backend& bk, int n)
             err = std::max(err, std::fabs(v - want));
         },
         Neon::computeMode_t::seq);
-    report("MAP axpy", err == 0.0, err);
+    size_t visited = 0;
+    y.forEachActiveCell([&](const Neon::index_3d&, const int& c, double&) { visited += c == 0; }, Neon::computeMode_t::seq);
+    report((std::string("MAP axpy on ") + gridName + " (" + std::to_string(visited) + " active cells)").c_str(),
+           err == 0.0 && visited == grid.getNumActiveCells(), err);
     if (axpy.getTokens().size() != 2 || axpy.getTokens()[0].access != Neon::set::Access::read ||
         axpy.getTokens()[1].access != Neon::set::Access::write) {
         report("MAP tokens (const field = read, non-const = write)", false, 0);
@@ -68,13 +80,14 @@ void testAxpy(const Neon::Backend& bk, int n)
 }
 
 // ------------------------------------------------------------------------------------------------------ 2. STENCIL
-void testDiffusion(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, Neon::set::TransferMode mode)
+template <typename Grid>
+void testDiffusion(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, Neon::set::TransferMode mode, const char* gridName)
 {
-    using Field = Neon::dGrid::Field<double, 1>;
+    using Field = typename Grid::template Field<double, 1>;
     const std::vector<Neon::index_3d> star = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
-    const Neon::index_3d              dim(n + 2, n, n + 5);
-    Neon::dGrid                       grid(bk, dim, [](const Neon::index_3d&) { return true; }, star);
-    Field                             u[2] = {grid.newField<double, 1>("u0", 1, 0.0), grid.newField<double, 1>("u1", 1, 0.0)};
+    const Neon::index_3d              dim(n + 2, n, std::max(n + 5, 16 * bk.getDeviceCount() + 3));
+    Grid                              grid(bk, dim, [](const Neon::index_3d&) { return true; }, star);
+    Field                             u[2] = {grid.template newField<double, 1>("u0", 1, 0.0), grid.template newField<double, 1>("u1", 1, 0.0)};
     auto                              init = [](const Neon::index_3d& p, const int&, double& v) { v = std::sin(0.3 * p.x) + 0.1 * p.y * p.z; };
     u[0].forEachActiveCell(init);
     u[0].updateDeviceData();
@@ -86,7 +99,7 @@ void testDiffusion(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, Neon
         auto         step = grid.newContainer("diffusion", [&](Neon::set::Loader& L) {
             const auto& a = L.load(in, Neon::Pattern::STENCIL);
             auto&       b = L.load(out);
-            return [=] NEON_CUDA_HOST_DEVICE(const Neon::dGrid::Idx& i) mutable {
+            return [=] NEON_CUDA_HOST_DEVICE(const typename Grid::Idx& i) mutable {
                 const double c = a(i, 0);
                 /* missing neighbours (outside the box) take the cell's own value: zero-flux walls */
                 const double s = a.template getNghData<-1, 0, 0>(i, 0, c) + a.template getNghData<1, 0, 0>(i, 0, c) +
@@ -95,7 +108,7 @@ void testDiffusion(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, Neon
                 b(i, 0) = c + k * (s - 6.0 * c);
             };
         });
-        sk[t].sequence({step}, "diffusion", Neon::skeleton::Options(occ, mode));
+        sk[t].sequence(std::vector<Neon::set::Container>{step}, "diffusion", Neon::skeleton::Options(occ, mode));
     }
     const int iters = 7;
     for (int it = 0; it < iters; ++it) {
@@ -135,21 +148,128 @@ void testDiffusion(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, Neon
             scale = std::max(scale, std::fabs(at(a, p.x, p.y, p.z)));
         },
         Neon::computeMode_t::seq);
-    const std::string name = std::string("STENCIL diffusion, OCC ") + Neon::skeleton::OccUtils::toString(occ) + ", " +
+    const std::string name = std::string("STENCIL diffusion on ") + gridName + ", OCC " + Neon::skeleton::OccUtils::toString(occ) + ", " +
                              Neon::set::TransferModeUtils::toString(mode);
     report(name.c_str(), err <= 1e-13 * scale, err / scale);
 }
 
+// ------------------------------------------------------------------------------------- 2b. map -> stencil -> map sequence
+// One Skeleton holding three containers (the shape Occ::extended / Occ::twoWayExtended transform, multiGpuGraph.cpp:145-301):
+// b = 2a + 1 (map), c = z-stencil of b (stencil), a = 0.25 c - b (map; feeds the next run).  Compared with the host.
+void testSequence(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ)
+{
+    using Field = Neon::dGrid::Field<double, 1>;
+    const std::vector<Neon::index_3d> zstar = {{0, 0, -1}, {0, 0, 1}};
+    const Neon::index_3d              dim(n, n / 2 + 1, std::max(n + 3, 6 * bk.getDeviceCount()));
+    Neon::dGrid                       grid(bk, dim, [](const Neon::index_3d&) { return true; }, zstar);
+    Field                             a = grid.newField<double, 1>("a", 1, 0.0), b = grid.newField<double, 1>("b", 1, 0.0), c = grid.newField<double, 1>("c", 1, 0.0);
+    auto                              init = [](const Neon::index_3d& p, const int&, double& v) { v = 0.01 * p.x - 0.02 * p.y + 0.001 * p.z * p.z; };
+    a.forEachActiveCell(init);
+    a.updateDeviceData();
+    auto m1 = grid.newContainer("M1", [&](Neon::set::Loader& L) {
+        const auto& ap = L.load(const_cast<const Field&>(a));
+        auto&       bp = L.load(b);
+        return [=] NEON_CUDA_HOST_DEVICE(const Neon::dGrid::Idx& i) mutable { bp(i, 0) = 2.0 * ap(i, 0) + 1.0; };
+    });
+    auto st = grid.newContainer("S", [&](Neon::set::Loader& L) {
+        const auto& bp = L.load(const_cast<const Field&>(b), Neon::Pattern::STENCIL);
+        auto&       cp = L.load(c);
+        return [=] NEON_CUDA_HOST_DEVICE(const Neon::dGrid::Idx& i) mutable {
+            cp(i, 0) = bp.template getNghData<0, 0, -1>(i, 0, 0.0) + 2.0 * bp(i, 0) + bp.template getNghData<0, 0, 1>(i, 0, 0.0);
+        };
+    });
+    auto m2 = grid.newContainer("M2", [&](Neon::set::Loader& L) {
+        const auto& cp = L.load(const_cast<const Field&>(c));
+        const auto& bp = L.load(const_cast<const Field&>(b));
+        auto&       ap = L.load(a);
+        return [=] NEON_CUDA_HOST_DEVICE(const Neon::dGrid::Idx& i) mutable { ap(i, 0) = 0.25 * cp(i, 0) - bp(i, 0); };
+    });
+    Neon::skeleton::Skeleton sk(bk);
+    sk.sequence({m1, st, m2}, "map-stencil-map", Neon::skeleton::Options(occ, Neon::set::TransferMode::get));
+    const int runs = 5;
+    for (int r = 0; r < runs; ++r) {
+        sk.run();
+    }
+    a.updateHostData();
+    bk.syncAll();
+    const size_t        cells = dim.rMul<size_t>();
+    std::vector<double> A(cells), B(cells), C(cells);
+    auto                at = [&](std::vector<double>& f, int x, int y, int z) -> double& { return f[(size_t(z) * dim.y + y) * dim.x + x]; };
+    for (int z = 0; z < dim.z; ++z)
+        for (int y = 0; y < dim.y; ++y)
+            for (int x = 0; x < dim.x; ++x) {
+                int k = 0;
+                init(Neon::index_3d(x, y, z), k, at(A, x, y, z));
+            }
+    for (int r = 0; r < runs; ++r) {
+        for (size_t i = 0; i < cells; ++i)
+            B[i] = 2.0 * A[i] + 1.0;
+        for (int z = 0; z < dim.z; ++z)
+            for (int y = 0; y < dim.y; ++y)
+                for (int x = 0; x < dim.x; ++x)
+                    at(C, x, y, z) = (z > 0 ? at(B, x, y, z - 1) : 0.0) + 2.0 * at(B, x, y, z) + (z + 1 < dim.z ? at(B, x, y, z + 1) : 0.0);
+        for (size_t i = 0; i < cells; ++i)
+            A[i] = 0.25 * C[i] - B[i];
+    }
+    double err = 0, scale = 0;
+    a.forEachActiveCell(
+        [&](const Neon::index_3d& p, const int&, double& v) {
+            err = std::max(err, std::fabs(v - at(A, p.x, p.y, p.z)));
+            scale = std::max(scale, std::fabs(at(A, p.x, p.y, p.z)));
+        },
+        Neon::computeMode_t::seq);
+    const std::string name = std::string("SEQUENCE map -> stencil -> map in one Skeleton, OCC ") + Neon::skeleton::OccUtils::toString(occ);
+    report(name.c_str(), err <= 1e-12 * scale, err / scale);
+}
+
 // ---------------------------------------------------------------------------------------------------------- 3. LBM
+// A D3Q19 pull-stream + BGK step written as a USER lambda, the way an application author writes it against Neon's API
+// (benchmarks/lbm-lid-driven-cavity-flow/src/LbmTools.h:99-282 does the same by macro expansion): one statement per
+// population with COMPILE-TIME neighbour offsets (getNghData<dx,dy,dz>), so the launcher's address arithmetic folds to
+// immediates on the padded pitch.  It is the workload that measures the generic launch path against the reference's.
 struct Lattice19
 {
-    int8_t c[19][3];
-    float  w[19];
+    /* D3Q19.h:23-44 numbering, opposite of k is k +- 10, rest population 9 */
+    NEON_CUDA_HOST_DEVICE static constexpr int c(int k, int d)
+    {
+        constexpr int t[19][3] = {{-1, 0, 0}, {0, -1, 0}, {0, 0, -1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {0, -1, -1}, {0, -1, 1}, {0, 0, 0},
+                                  {1, 0, 0},  {0, 1, 0},  {0, 0, 1},  {1, 1, 0},   {1, -1, 0}, {1, 0, 1},   {1, 0, -1}, {0, 1, 1},   {0, 1, -1}};
+        return t[k][d];
+    }
+    NEON_CUDA_HOST_DEVICE static constexpr int   opp(int k) { return k == 9 ? 9 : (k < 9 ? k + 10 : k - 10); }
+    NEON_CUDA_HOST_DEVICE static constexpr float w(int k) { return k == 9 ? 1.f / 3.f : ((k % 10) < 3 ? 1.f / 18.f : 1.f / 36.f); }
 };
+
+template <int K, typename Part>
+NEON_CUDA_HOST_DEVICE inline float pullOne(const Part& in, const Neon::dGrid::Idx& i, uint32_t word)
+{
+    using L = Lattice19;
+    constexpr int bx = -L::c(K, 0), by = -L::c(K, 1), bz = -L::c(K, 2);
+    if (K != 9 && (word & (1u << K))) { /* the cell at x - c_k is a wall: half-way bounce-back (+ lid momentum) */
+        return in(i, L::opp(K)) + in.template getNghData<bx, by, bz>(i, L::opp(K)).mData;
+    }
+    return in.template getNghData<bx, by, bz>(i, K).mData;
+}
+template <typename Part, int... Ks>
+NEON_CUDA_HOST_DEVICE inline void pullAll(std::integer_sequence<int, Ks...>, const Part& in, const Neon::dGrid::Idx& i, uint32_t word, float (&f)[19])
+{
+    ((f[Ks] = pullOne<Ks>(in, i, word)), ...);
+}
+template <typename Part, int... Ks>
+NEON_CUDA_HOST_DEVICE inline void collideAll(std::integer_sequence<int, Ks...>, Part& out, const Neon::dGrid::Idx& i, const float (&f)[19], float rho,
+                                             float ux, float uy, float uz, float usqr, float omega)
+{
+    using L = Lattice19;
+    ((out(i, Ks) = (1.f - omega) * f[Ks] +
+                   omega * (rho * L::w(Ks) *
+                            (1.f + 3.f * (L::c(Ks, 0) * ux + L::c(Ks, 1) * uy + L::c(Ks, 2) * uz) +
+                             4.5f * (L::c(Ks, 0) * ux + L::c(Ks, 1) * uy + L::c(Ks, 2) * uz) * (L::c(Ks, 0) * ux + L::c(Ks, 1) * uy + L::c(Ks, 2) * uz) - usqr))),
+     ...);
+}
 
 template <typename Pop, typename Flag>
 Neon::set::Container userLbmStep(const Neon::dGrid& grid, Neon::set::StencilSemantic semantic, const Pop& fIn, const Flag& flag, float omega,
-                                 Pop& fOut, const Lattice19& lat)
+                                 Pop& fOut)
 {
     return grid.newContainer("userLambdaLBM", [&](Neon::set::Loader& L) {
         const auto& in = L.load(fIn, Neon::Pattern::STENCIL, semantic);
@@ -161,31 +281,20 @@ Neon::set::Container userLbmStep(const Neon::dGrid& grid, Neon::set::StencilSema
                 return; /* non-bulk cells are never written (LbmTools.h:304) */
             }
             float f[19];
-            for (int k = 0; k < 19; ++k) {
-                const int            opp = k == 9 ? 9 : (k < 9 ? k + 10 : k - 10);
-                const Neon::index_3d back(-lat.c[k][0], -lat.c[k][1], -lat.c[k][2]);
-                if (word & (1u << k)) { /* the cell at x - c_k is a wall: half-way bounce-back (+ lid momentum) */
-                    f[k] = in(i, opp) + in.getNghData(i, back, opp).mData;
-                } else {
-                    f[k] = in.getNghData(i, back, k).mData;
-                }
-            }
+            pullAll(std::make_integer_sequence<int, 19>{}, in, i, word, f);
             float rho = 0, ux = 0, uy = 0, uz = 0;
+#pragma unroll
             for (int k = 0; k < 19; ++k) {
                 rho += f[k];
-                ux += f[k] * lat.c[k][0];
-                uy += f[k] * lat.c[k][1];
-                uz += f[k] * lat.c[k][2];
+                ux += f[k] * Lattice19::c(k, 0);
+                uy += f[k] * Lattice19::c(k, 1);
+                uz += f[k] * Lattice19::c(k, 2);
             }
             ux /= rho;
             uy /= rho;
             uz /= rho;
             const float usqr = 1.5f * (ux * ux + uy * uy + uz * uz);
-            for (int k = 0; k < 19; ++k) {
-                const float cu = 3.f * (lat.c[k][0] * ux + lat.c[k][1] * uy + lat.c[k][2] * uz);
-                const float eq = rho * lat.w[k] * (1.f + cu + 0.5f * cu * cu - usqr);
-                out(i, k) = (1.f - omega) * f[k] + omega * eq;
-            }
+            collideAll(std::make_integer_sequence<int, 19>{}, out, i, f, rho, ux, uy, uz, usqr, omega);
         };
     });
 }
@@ -200,12 +309,12 @@ void testLbm(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, int benchI
     Pop                  a0 = grid.newField<float, 19>("a0", 19, 0.f), a1 = grid.newField<float, 19>("a1", 19, 0.f);
     Pop                  b0 = grid.newField<float, 19>("b0", 19, 0.f), b1 = grid.newField<float, 19>("b1", 19, 0.f);
     auto                 flag = grid.newField<CellType, 1>("flag", 1, CellType());
-    Lattice19            lat{};
-    for (int k = 0; k < 19; ++k) {
+    for (int k = 0; k < 19; ++k) { /* the compile-time table of the user lambda is the benchmark's lattice */
         for (int d = 0; d < 3; ++d) {
-            lat.c[k][d] = int8_t(lattice.c_vect[k].v[d]);
+            if (Lattice19::c(k, d) != lattice.c_vect[k].v[d]) {
+                report("lattice table of the user lambda", false, 0);
+            }
         }
-        lat.w[k] = float(lattice.t_vect[k]);
     }
     const double nu = 0.04 * double(n - 2) / 100.0;
     const float  omega = float(1. / (3. * nu + 0.5));
@@ -228,8 +337,8 @@ void testLbm(const Neon::Backend& bk, int n, Neon::skeleton::Occ occ, int benchI
     bk.syncAll();
     const auto               sem = Neon::set::StencilSemantic::streaming;
     Neon::skeleton::Skeleton user[2] = {Neon::skeleton::Skeleton(bk), Neon::skeleton::Skeleton(bk)};
-    user[0].sequence({userLbmStep(grid, sem, const_cast<const Pop&>(a0), flag, omega, a1, lat)}, "user0", Neon::skeleton::Options(occ, Neon::set::TransferMode::get));
-    user[1].sequence({userLbmStep(grid, sem, const_cast<const Pop&>(a1), flag, omega, a0, lat)}, "user1", Neon::skeleton::Options(occ, Neon::set::TransferMode::get));
+    user[0].sequence({userLbmStep(grid, sem, const_cast<const Pop&>(a0), flag, omega, a1)}, "user0", Neon::skeleton::Options(occ, Neon::set::TransferMode::get));
+    user[1].sequence({userLbmStep(grid, sem, const_cast<const Pop&>(a1), flag, omega, a0)}, "user1", Neon::skeleton::Options(occ, Neon::set::TransferMode::get));
     LbmIterationD3Q19<Pop, float> native(sem, occ, Neon::set::TransferMode::get, b0, b1, flag, omega);
     const int iters = benchIters ? benchIters : 20;
     auto      timeIt = [&](auto&& body) {
@@ -307,11 +416,14 @@ int main(int argc, char** argv)
         if (bench) {
             testLbm(bk, bench, Neon::skeleton::Occ::standard, 50);
         } else {
-            testAxpy(bk, n);
-            for (auto occ : {Neon::skeleton::Occ::none, Neon::skeleton::Occ::standard}) {
+            testAxpy<Neon::dGrid>(bk, n, "dGrid");
+            testAxpy<Neon::bGrid>(bk, n, "bGrid");
+            for (auto occ : {Neon::skeleton::Occ::none, Neon::skeleton::Occ::standard, Neon::skeleton::Occ::extended, Neon::skeleton::Occ::twoWayExtended}) {
                 for (auto mode : {Neon::set::TransferMode::get, Neon::set::TransferMode::put}) {
-                    testDiffusion(bk, n, occ, mode);
+                    testDiffusion<Neon::dGrid>(bk, n, occ, mode, "dGrid");
+                    testDiffusion<Neon::bGrid>(bk, n, occ, mode, "bGrid");
                 }
+                testSequence(bk, n, occ);
                 testLbm(bk, n, occ, 0);
             }
         }

@@ -7,13 +7,16 @@
 // Differences by design: the loading lambda is parsed ONCE per device when the container is built (the reference
 // re-runs it at every launch) and the launch goes straight to cudaLaunch (the reference calls cudaFuncGetAttributes on
 // every launch, libNeonSys/include/Neon/sys/devices/gpu/GpuDevice.h:151-191), so a Skeleton of such containers can be
-// captured into a CUDA graph.  This header needs nvcc (--extended-lambda); the LBM hot path does not use it.
+// captured into a CUDA graph.  bGrid::newContainer does the same over the blocks of a view (LambdaExecutor.h:105-116,
+// bSpan_imp.h:7-21, bPartition_imp.h:97-124,194-198,340-358).  This header needs nvcc (--extended-lambda); the LBM hot path
+// does not use it.
 #pragma once
 
 #ifndef __CUDACC__
 #error "Neon/domain/GenericContainer.h defines device kernels: include it from a .cu translation unit (nvcc --extended-lambda)"
 #endif
 
+#include "Neon/domain/bGrid.h"
 #include "Neon/domain/dGrid.h"
 
 namespace Neon::detail {
@@ -48,9 +51,55 @@ struct SpanLauncher
     }
 };
 
+/* block-sparse grids: one CUDA block of 8 x 8 x 8 threads per block of the view (the reference launches 512-thread blocks
+ * the same way, bSpan_imp.h:7-21) */
+template <typename UserLambda>
+__global__ void __launch_bounds__(512) neonLambdaOnBlocks(const bSpan span, UserLambda userLambda)
+{
+    bIdx idx;
+    if (span.setAndValidate(idx, blockIdx.x, int(threadIdx.x), int(threadIdx.y), int(threadIdx.z))) {
+        userLambda(idx);
+    }
+}
+template <typename UserLambda>
+struct BlockLauncher
+{
+    UserLambda fn;
+    explicit BlockLauncher(const UserLambda& f) : fn(f) {}
+    void launch(const bSpan& span, cudaStream_t stream) const
+    {
+        if (span.nBlocksView() == 0) {
+            return;
+        }
+        neonLambdaOnBlocks<UserLambda><<<span.nBlocksView(), dim3(8, 8, 8), 0, stream>>>(span, fn);
+        NEON_CUDA_CHECK(cudaGetLastError());
+    }
+};
+
 }  // namespace Neon::detail
 
 namespace Neon {
+
+template <typename LoadingLambda>
+set::Container bGrid::newContainer(const std::string& name, LoadingLambda loadingLambda) const
+{
+    auto impl = std::make_shared<set::detail::DeviceManagedImpl>();
+    impl->name = name;
+    impl->backend = getBackend();
+    impl->genericBody = true;
+    const Backend bk = getBackend();
+    const bGrid   grid = *this;
+    for (int d = 0; d < bk.getDeviceCount(); ++d) {
+        set::Loader loader(d, &impl->tokens);
+        auto        userLambda = loadingLambda(loader);
+        using Launcher = detail::BlockLauncher<decltype(userLambda)>;
+        auto launcher = std::make_shared<Launcher>(userLambda);
+        impl->launchers.emplace_back([launcher, grid, bk, d](int streamIdx, DataView dataView) {
+            launcher->launch(grid.getSpan(d, dataView), bk.stream(d, streamIdx));
+        });
+    }
+    return set::Container(impl);
+}
 
 template <typename LoadingLambda>
 set::Container dGrid::newContainer(const std::string& name, LoadingLambda loadingLambda) const

@@ -62,11 +62,48 @@ struct bGridState
 
 }  // namespace detail
 
+/* a cell of a block-sparse partition: block + position inside the 8 x 8 x 8 tile (the reference's bIndex, bIndex.h) */
+struct bIdx
+{
+    uint32_t blk = 0;
+    int32_t  x = 0, y = 0, z = 0;
+};
+
+/* the blocks a generic container visits for one data view, and what decides whether a cell of them exists
+ * (the reference's bSpan, bSpan_imp.h:7-21: block id from the CUDA block, cell from the thread, active bit from the mask) */
+struct bSpan
+{
+    using Idx = bIdx;
+    uint32_t        first[2] = {0, 0}, count[2] = {0, 0}; /* up to two block ranges: BOUNDARY = lowest + highest layer */
+    const uint32_t* info = nullptr;                        /* [block][32]: 27 neighbour ids + origin */
+    const uint32_t* activeMask = nullptr;                  /* [block][16] or null: every cell inside the box is active */
+    int32_t         gnx = 0, gny = 0, gnz = 0;
+    uint32_t        nBlocksView() const { return count[0] + count[1]; }
+    NEON_CUDA_HOST_DEVICE bool setAndValidate(bIdx& idx, uint32_t viewBlock, int x, int y, int z) const
+    {
+        if (viewBlock >= count[0] + count[1]) {
+            return false;
+        }
+        idx.blk = viewBlock < count[0] ? first[0] + viewBlock : first[1] + (viewBlock - count[0]);
+        idx.x = x;
+        idx.y = y;
+        idx.z = z;
+        const uint32_t* line = info + size_t(idx.blk) * 32;
+        if (int(line[27]) + x >= gnx || int(line[28]) + y >= gny || int(line[29]) + z >= gnz) {
+            return false;
+        }
+        const int c = (z * detail::kB + y) * detail::kB + x;
+        return activeMask == nullptr || ((activeMask[size_t(idx.blk) * 16 + (c >> 5)] >> (c & 31)) & 1u);
+    }
+};
+
 class bGrid
 {
    public:
     template <typename T, int C = 0>
     using Field = bField<T, C>;
+    using Span = bSpan;
+    using Idx = bIdx;
     static constexpr int blockEdge = detail::kB;
 
     bGrid() = default;
@@ -256,6 +293,35 @@ class bGrid
         return bField<T, C>(*this, name, cardinality, outsideValue, mS->nextUid++);
     }
 
+    /* blocks of a data view: STANDARD every local block, BOUNDARY the lowest and highest block layer of the partition (the
+     * ones whose faces the halo update moves), INTERNAL the rest — the block ranges the LBM step kernel uses */
+    bSpan getSpan(int setIdx, DataView dataView) const
+    {
+        const auto& p = mS->parts.at(setIdx);
+        bSpan       sp;
+        sp.info = p.infoDev;
+        sp.activeMask = p.activeMaskDev;
+        sp.gnx = mS->dim.x;
+        sp.gny = mS->dim.y;
+        sp.gnz = mS->dim.z;
+        if (dataView == DataView::STANDARD) {
+            sp.count[0] = p.nBlocks;
+        } else if (dataView == DataView::INTERNAL) {
+            sp.first[0] = p.nDown;
+            sp.count[0] = p.nBlocks - p.nDown - p.nUp;
+        } else {
+            sp.count[0] = p.nDown;
+            sp.first[1] = p.nBlocks - p.nUp;
+            sp.count[1] = p.nUp;
+        }
+        return sp;
+    }
+
+    /* Grid::newContainer(name, loadingLambda): per-cell device lambdas over the active cells of the blocks of a data view
+     * (LambdaExecutor.h:105-116, bSpan_imp.h:7-21).  Needs nvcc: include "Neon/domain/GenericContainer.h" from a .cu file. */
+    template <typename LoadingLambda>
+    set::Container newContainer(const std::string& name, LoadingLambda loadingLambda) const;
+
    private:
     std::shared_ptr<detail::bGridState> mS;
 };
@@ -358,12 +424,78 @@ class bField
     /* the reference's bPartition (bPartition.h:154-160) without the per-cell accessors the C ABI replaces */
     struct Partition
     {
+        using Idx = bIdx;
+        using Type = DeviceType;
         DeviceType*     memory = nullptr;
         nlbm_block_desc desc{};
         int             card = 0;
-        DeviceType*     mem() const { return memory; }
-        int             cardinality() const { return card; }
+        const uint32_t* activeMask = nullptr; /* [block][16] or null */
+        DeviceType      outsideValue{};
+        NEON_CUDA_HOST_DEVICE DeviceType* mem() const { return memory; }
+        NEON_CUDA_HOST_DEVICE int         cardinality() const { return card; }
+
+        /* per-cell accessors for generic device lambdas (bPartition_imp.h:97-124, 194-198, 340-358), on the layout of this
+         * library: pop[c][blk][z][y][x], 64-bit offsets */
+        NEON_CUDA_HOST_DEVICE size_t offset(uint32_t blk, int x, int y, int z, int c) const
+        {
+            return (size_t(c) * desc.n_blocks_alloc + blk) * detail::kBlockCells + size_t((z * detail::kB + y) * detail::kB + x);
+        }
+        NEON_CUDA_HOST_DEVICE DeviceType& operator()(const bIdx& i, int c) const { return memory[offset(i.blk, i.x, i.y, i.z, c)]; }
+        NEON_CUDA_HOST_DEVICE index_3d    getGlobalIndex(const bIdx& i) const
+        {
+            const uint32_t* line = static_cast<const uint32_t*>(desc.info) + size_t(i.blk) * 32;
+            return {int(line[27]) + i.x, int(line[28]) + i.y, int(line[29]) + i.z};
+        }
+        /* the neighbour cell: inside the same tile, or in the tile the block's connectivity line names (a ghost block at a
+         * partition face); it exists if that tile exists, the cell lies inside the box and is active */
+        NEON_CUDA_HOST_DEVICE bool locate(const bIdx& i, int dx, int dy, int dz, uint32_t& blk, int& x, int& y, int& z) const
+        {
+            x = i.x + dx;
+            y = i.y + dy;
+            z = i.z + dz;
+            const int fx = x < 0 ? -1 : (x >= detail::kB ? 1 : 0), fy = y < 0 ? -1 : (y >= detail::kB ? 1 : 0),
+                      fz = z < 0 ? -1 : (z >= detail::kB ? 1 : 0);
+            blk = i.blk;
+            const uint32_t* info = static_cast<const uint32_t*>(desc.info);
+            if (fx | fy | fz) {
+                blk = info[size_t(i.blk) * 32 + (fx + 1) + 3 * (fy + 1) + 9 * (fz + 1)];
+                if (blk == NLBM_NO_BLOCK) {
+                    return false;
+                }
+                x -= detail::kB * fx;
+                y -= detail::kB * fy;
+                z -= detail::kB * fz;
+            }
+            const uint32_t* line = info + size_t(blk) * 32;
+            if (int(line[27]) + x >= desc.gnx || int(line[28]) + y >= desc.gny || int(line[29]) + z >= desc.gnz) {
+                return false;
+            }
+            const int c = (z * detail::kB + y) * detail::kB + x;
+            return activeMask == nullptr || ((activeMask[size_t(blk) * 16 + (c >> 5)] >> (c & 31)) & 1u);
+        }
+        NEON_CUDA_HOST_DEVICE domain::NghData<DeviceType> getNghData(const bIdx& i, const index_3d& off, int c) const
+        {
+            domain::NghData<DeviceType> r;
+            uint32_t                    blk;
+            int                         x, y, z;
+            r.mIsValid = locate(i, off.x, off.y, off.z, blk, x, y, z);
+            r.mData = r.mIsValid ? memory[offset(blk, x, y, z, c)] : outsideValue;
+            return r;
+        }
+        template <int dx, int dy, int dz>
+        NEON_CUDA_HOST_DEVICE domain::NghData<DeviceType> getNghData(const bIdx& i, int c) const
+        {
+            return getNghData(i, index_3d(dx, dy, dz), c);
+        }
+        template <int dx, int dy, int dz>
+        NEON_CUDA_HOST_DEVICE DeviceType getNghData(const bIdx& i, int c, DeviceType alternative) const
+        {
+            uint32_t blk;
+            int      x, y, z;
+            return locate(i, dx, dy, dz, blk, x, y, z) ? memory[offset(blk, x, y, z, c)] : alternative;
+        }
     };
+    using Idx = bIdx;
 
     bField() = default;
 
@@ -539,6 +671,10 @@ class bField
             part.memory = static_cast<DeviceType*>(p);
             part.desc = grid.descOf(d);
             part.card = cardinality;
+            part.activeMask = grid.activeMaskDev(d);
+            if constexpr (!kFlagWords) {
+                part.outsideValue = outside;
+            }
             s.parts.push_back(part);
         }
     }

@@ -130,7 +130,7 @@ int smCount()
 }
 
 int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, double omega, int view, int opts, void* stream,
-             const nlbm_peer_desc* peer = nullptr)
+             const nlbm_peer_desc* peer = nullptr, int iterations = 0, const void* wallCacheIn = nullptr)
 {
     if (int rc = checkDesc(d, elemBytes, true, true, true))
         return rc;
@@ -245,6 +245,18 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
         return fail(NLBM_ERR_INVALID, "bad kernel selector %d", kernelSel);
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (iterations > 0) {  // nlbm_dense_step_n: several iterations, the two fields swapping roles, in one cooperative launch
+        if (view != NLBM_VIEW_STANDARD || peer != nullptr || l.tmapA != nullptr)
+            return fail(NLBM_ERR_INVALID, "multi-iteration launch: STANDARD view, direct kernel, no face push");
+        nlbm::MultiArgs m{};
+        m.fieldB = d->pop_out;
+        m.keepCacheA = wallCacheIn;
+        m.iterations = iterations;
+        cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchMultiRef(kind, a, m, l, st) : nlbm::launchMultiFast(kind, a, m, l, st);
+        if (e != cudaSuccess)
+            return cudaFail(e, "dense multi-iteration launch");
+        return NLBM_OK;
+    }
     cudaError_t  e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchStepRef(kind, a, l, st) : nlbm::launchStepFast(kind, a, l, st);
     if (e != cudaSuccess)
         return cudaFail(e, "dense step launch");
@@ -434,6 +446,18 @@ int nlbm_d3q27_f32_dense_step(const nlbm_dense_desc* d, double omega, int data_v
 int nlbm_d3q27_f64_dense_step(const nlbm_dense_desc* d, double omega, int data_view, int opts, void* stream)
 {
     return stepImpl(nlbm::kD3Q27_F64, 8, d, omega, data_view, opts, stream);
+}
+
+int nlbm_dense_step_n(int kind, const nlbm_dense_desc* d, const void* wall_cache_in, double omega, int iterations, int opts, void* stream)
+{
+    if (kind < 0 || kind > 4)
+        return fail(NLBM_ERR_INVALID, "bad step kind %d", kind);
+    if (iterations < 1)
+        return fail(NLBM_ERR_INVALID, "iterations must be >= 1");
+    if (!d || d->z_halo != 0)
+        return fail(NLBM_ERR_UNSUPPORTED, "multi-iteration launch needs a partition without neighbours (z_halo = 0): nothing is exchanged between its iterations");
+    const int elem = (kind == nlbm::kD3Q19_F64 || kind == nlbm::kD3Q27_F64) ? 8 : 4;
+    return stepImpl((nlbm::StepKind)kind, elem, d, omega, NLBM_VIEW_STANDARD, opts, stream, nullptr, iterations, wall_cache_in);
 }
 
 int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream)

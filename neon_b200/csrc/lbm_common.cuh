@@ -136,6 +136,15 @@ struct DenseArgs
     uint32_t  signalValue, warpsPerFace;
 };
 
+// second argument of the multi-iteration kernel (k_dense_multi, lbm_step.cuh)
+struct MultiArgs
+{
+    const void* fieldB;      // the second field: iteration t reads (t even ? a.in : fieldB) and writes the other one
+    const void* keepCacheA;  // x-face cache of a.in (a.keepCache is a.out's, i.e. fieldB's); may be null like a.keepCache
+    int32_t     iterations;
+    uint32_t    gx, gy, gz;  // the step kernel's launch grid: tiles to walk
+};
+
 // ---------------------------------------------------------------- vector access
 template <typename T, int VEC>
 struct Vec;
@@ -215,6 +224,62 @@ __device__ __forceinline__ double ldPred1(const double* p, bool pred)
     ldPred(p, pred, v);
     return v[0];
 }
+// The same loads served from L2 (ld.global.cg): for the multi-iteration kernel, where the field a thread reads was written
+// by other SMs earlier in the SAME launch — the non-coherent path (and L1) may still hold the values of two iterations ago.
+__device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[4])
+{
+    asm volatile(
+        "{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\n"
+        "mov.f32 %3, 0f00000000;\n@q ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n}\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+        : "l"(p), "r"((uint32_t)pred)
+        : "memory");
+}
+__device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[2])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\n"
+                 "@q ld.global.cg.v2.f32 {%0, %1}, [%2];\n}\n"
+                 : "=f"(v[0]), "=f"(v[1])
+                 : "l"(p), "r"((uint32_t)pred)
+                 : "memory");
+}
+__device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[1])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f32 %0, 0f00000000;\n@q ld.global.cg.f32 %0, [%1];\n}\n"
+                 : "=f"(v[0])
+                 : "l"(p), "r"((uint32_t)pred)
+                 : "memory");
+}
+__device__ __forceinline__ void ldPredCg(const double* p, bool pred, double (&v)[2])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f64 %0, 0d0000000000000000;\nmov.f64 %1, 0d0000000000000000;\n"
+                 "@q ld.global.cg.v2.f64 {%0, %1}, [%2];\n}\n"
+                 : "=d"(v[0]), "=d"(v[1])
+                 : "l"(p), "r"((uint32_t)pred)
+                 : "memory");
+}
+__device__ __forceinline__ void ldPredCg(const double* p, bool pred, double (&v)[1])
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.cg.f64 %0, [%1];\n}\n"
+                 : "=d"(v[0])
+                 : "l"(p), "r"((uint32_t)pred)
+                 : "memory");
+}
+template <bool COH, typename T, int N>
+__device__ __forceinline__ void ldPredSel(const T* p, bool pred, T (&v)[N])
+{
+    if constexpr (COH)
+        ldPredCg(p, pred, v);
+    else
+        ldPred(p, pred, v);
+}
+template <bool COH, typename T>
+__device__ __forceinline__ T ldPredSel1(const T* p, bool pred)
+{
+    T v[1];
+    ldPredSel<COH>(p, pred, v);
+    return v[0];
+}
 // coherent variants (the output field: cells this kernel never writes, but next to cells it does)
 __device__ __forceinline__ float ldPredCoherent1(const float* p, bool pred, float keep)
 {
@@ -237,6 +302,24 @@ __device__ __forceinline__ double ldPredKeepNc1(const double* p, bool pred, doub
 {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.nc.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
     return keep;
+}
+__device__ __forceinline__ float ldPredKeepCg1(const float* p, bool pred, float keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.cg.f32 %0, [%1];\n}\n" : "+f"(keep) : "l"(p), "r"((uint32_t)pred) : "memory");
+    return keep;
+}
+__device__ __forceinline__ double ldPredKeepCg1(const double* p, bool pred, double keep)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.cg.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred) : "memory");
+    return keep;
+}
+template <bool COH, typename T>
+__device__ __forceinline__ T ldPredKeepSel1(const T* p, bool pred, T keep)
+{
+    if constexpr (COH)
+        return ldPredKeepCg1(p, pred, keep);
+    else
+        return ldPredKeepNc1(p, pred, keep);
 }
 // asynchronous copy of one element from global to shared memory: no destination register, nobody waits until cpAsyncWait
 __device__ __forceinline__ void cpAsync1(float* smem, const float* gmem)

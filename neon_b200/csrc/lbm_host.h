@@ -26,6 +26,10 @@ struct StepLaunch
 };
 cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
 cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
+// several iterations in one cooperative launch (direct kernel only); m names the second field
+struct MultiArgs;
+cudaError_t launchMultiRef(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st);
+cudaError_t launchMultiFast(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st);
 cudaError_t launchSelftestExact(int kind, unsigned long long n, unsigned long long seed, unsigned long long* dBad, cudaStream_t st);
 // tile width / rows of the TMA kernel for a population of elemBytes and a row of nx cells
 void tmaTileShape(int elemBytes, int nx, int* tx, int* ty);

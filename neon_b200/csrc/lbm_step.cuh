@@ -17,6 +17,8 @@
 //    per-cell fix-up executed only by cells whose wallNghBitflag is non-zero.
 //  * results leave through 16-byte streaming stores; non-bulk cells are never written (LbmTools.h:304).
 #pragma once
+#include <cooperative_groups.h>
+
 #include <type_traits>
 #include <utility>
 
@@ -358,7 +360,7 @@ struct CollideD3Q27Fast
 // Two phases so that EVERY global load of a thread is in flight before the first one is consumed: loadOne issues the
 // aligned 16-byte row load (and, on the two edge lanes of populations with c_x != 0, the one scalar the warp shuffle
 // cannot supply); shiftOne then realises the x shift in registers.
-template <class L, int q, typename T, int VEC>
+template <class L, int q, typename T, int VEC, bool COH = false>
 __device__ __forceinline__ void loadOne(const T* __restrict__ cell0, const DenseArgs& a, const int x0, const int y, const int zm,
                                         const int tx, const int lpr, const bool rowOk, T (&v)[VEC], T& edge)
 {
@@ -367,12 +369,12 @@ __device__ __forceinline__ void loadOne(const T* __restrict__ cell0, const Dense
     // rows outside the allocation are never dereferenced (an enclosed geometry has no bulk cell there)
     const bool ok = rowOk && (cy == 0 || (unsigned)ys < (unsigned)a.ny) && (cz == 0 || (unsigned)zs < (unsigned)a.nzm);
     const T*   p = cell0 + (q * a.pitch_q - cz * a.pitch_z - (int64_t)cy * a.pitch_y);
-    ldPred(p, ok, v);
+    ldPredSel<COH>(p, ok, v);
     edge = T(0);
     if constexpr (cx == 1)
-        edge = ldPred1(p - 1, tx == 0 && ok && x0 > 0);
+        edge = ldPredSel1<COH>(p - 1, tx == 0 && ok && x0 > 0);
     else if constexpr (cx == -1)
-        edge = ldPred1(p + VEC, tx == lpr - 1 && ok && x0 + VEC < a.pitch_y);
+        edge = ldPredSel1<COH>(p + VEC, tx == lpr - 1 && ok && x0 + VEC < a.pitch_y);
 }
 
 template <class L, int q, typename T, int VEC>
@@ -398,12 +400,12 @@ __device__ __forceinline__ void shiftOne(const int tx, const int lpr, T (&v)[VEC
     }
 }
 
-template <class L, typename T, int VEC, int... Qs>
+template <class L, typename T, int VEC, bool COH = false, int... Qs>
 __device__ __forceinline__ void loadAll(std::integer_sequence<int, Qs...>, const T* __restrict__ cell0, const DenseArgs& a,
                                         const int x0, const int y, const int zm, const int tx, const int lpr, const bool rowOk,
                                         T (&f)[L::Q][VEC], T (&edge)[L::Q])
 {
-    (loadOne<L, Qs, T, VEC>(cell0, a, x0, y, zm, tx, lpr, rowOk, f[Qs], edge[Qs]), ...);
+    (loadOne<L, Qs, T, VEC, COH>(cell0, a, x0, y, zm, tx, lpr, rowOk, f[Qs], edge[Qs]), ...);
 }
 template <class L, typename T, int VEC, int... Qs>
 __device__ __forceinline__ void shiftAll(std::integer_sequence<int, Qs...>, const int tx, const int lpr, T (&f)[L::Q][VEC],
@@ -436,7 +438,7 @@ struct Pairs
     }
 };
 
-template <class L, typename T, int VEC, int P>
+template <class L, typename T, int VEC, int P, bool COH = false>
 __device__ __forceinline__ void fixLoad(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i,
                                         T (&f)[L::Q][VEC], T& tb)
 {
@@ -449,11 +451,11 @@ __device__ __forceinline__ void fixLoad(const T* __restrict__ cell, const DenseA
     // serialised round trips per x-wall cell, 1.8x the time of the streaming loads).
     const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
     const T*      src = cell + (bq ? o : q) * a.pitch_q;
-    f[q][i] = ldPredKeepNc1(src, bq, f[q][i]);
-    f[o][i] = ldPredKeepNc1(src, bo && !bq, f[o][i]);
-    tb = ldPred1(bq ? src - dn : src + dn, bq || bo);
+    f[q][i] = ldPredKeepSel1<COH>(src, bq, f[q][i]);
+    f[o][i] = ldPredKeepSel1<COH>(src, bo && !bq, f[o][i]);
+    tb = ldPredSel1<COH>(bq ? src - dn : src + dn, bq || bo);
 }
-template <class L, typename T, int VEC, int P>
+template <class L, typename T, int VEC, int P, bool COH = false>
 __device__ __forceinline__ void fixUse(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i, const T tb,
                                        T (&f)[L::Q][VEC])
 {
@@ -466,33 +468,33 @@ __device__ __forceinline__ void fixUse(const T* __restrict__ cell, const DenseAr
     if (bq && bo) {  // walls on both sides of the cell along c_q: the second one is fetched late
         const int64_t dn = L::c(q, 2) * a.pitch_z + (int64_t)L::c(q, 1) * a.pitch_y + L::c(q, 0);
         const T*      src = cell + q * a.pitch_q;
-        f[o][i] = __ldg(src) + __ldg(src + dn);
+        f[o][i] = ldPredSel1<COH>(src, true) + ldPredSel1<COH>(src + dn, true);
     }
 }
 
-template <class L, typename T, int VEC, int P0, int P1, int... Ps>
+template <class L, typename T, int VEC, int P0, int P1, bool COH, int... Ps>
 __device__ __forceinline__ void fixChunk(std::integer_sequence<int, Ps...>, const T* __restrict__ cell, const DenseArgs& a,
                                          const uint32_t m, const int i, T (&f)[L::Q][VEC])
 {
     constexpr int N = P1 - P0;
     T             tb[N];
-    (fixLoad<L, T, VEC, P0 + Ps>(cell, a, m, i, f, tb[Ps]), ...);      // pass 1: every load of the chunk
-    (fixUse<L, T, VEC, P0 + Ps>(cell, a, m, i, tb[Ps], f), ...);       // pass 2: use them
+    (fixLoad<L, T, VEC, P0 + Ps, COH>(cell, a, m, i, f, tb[Ps]), ...);      // pass 1: every load of the chunk
+    (fixUse<L, T, VEC, P0 + Ps, COH>(cell, a, m, i, tb[Ps], f), ...);       // pass 2: use them
 }
 
 // CH = pairs per batch: CH temporaries live next to the Q*VEC values
-template <class L, typename T, int VEC, int CH>
+template <class L, typename T, int VEC, int CH, bool COH = false>
 __device__ __forceinline__ void fixCell(const T* __restrict__ cell, const DenseArgs& a, const uint32_t m, const int i,
                                         T (&f)[L::Q][VEC])
 {
     constexpr int NP = Pairs<L>::N;
     if constexpr (NP > 0 * CH)
-        fixChunk<L, T, VEC, 0, (NP < CH ? NP : CH)>(std::make_integer_sequence<int, (NP < CH ? NP : CH)>{}, cell, a, m, i, f);
+        fixChunk<L, T, VEC, 0, (NP < CH ? NP : CH), COH>(std::make_integer_sequence<int, (NP < CH ? NP : CH)>{}, cell, a, m, i, f);
     if constexpr (NP > 1 * CH)
-        fixChunk<L, T, VEC, CH, (NP < 2 * CH ? NP : 2 * CH)>(std::make_integer_sequence<int, (NP < 2 * CH ? NP : 2 * CH) - CH>{}, cell,
-                                                             a, m, i, f);
+        fixChunk<L, T, VEC, CH, (NP < 2 * CH ? NP : 2 * CH), COH>(std::make_integer_sequence<int, (NP < 2 * CH ? NP : 2 * CH) - CH>{}, cell,
+                                                                  a, m, i, f);
     if constexpr (NP > 2 * CH)
-        fixChunk<L, T, VEC, 2 * CH, NP>(std::make_integer_sequence<int, NP - 2 * CH>{}, cell, a, m, i, f);
+        fixChunk<L, T, VEC, 2 * CH, NP, COH>(std::make_integer_sequence<int, NP - 2 * CH>{}, cell, a, m, i, f);
     static_assert(NP <= 3 * CH, "chunking covers three batches");
 }
 
@@ -558,7 +560,7 @@ __device__ __forceinline__ void xFixUse(std::integer_sequence<int, Ks...>, const
 }
 
 // Wall fix-ups, collision and stores of the VEC cells one thread owns (shared by the direct and the TMA kernel).
-template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5)>
+template <class COL, typename T, int VEC, int CH = (sizeof(T) == 4 ? 9 : 5), bool COH = false>
 __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restrict__ cell0, T* __restrict__ out0,
                                             const uint32_t (&fl)[VEC], const bool special, T (&f)[COL::Q][VEC],
                                             T* __restrict__ peerDst = nullptr, const int64_t peerPitchQ = 0, const int peerDir = 0,
@@ -604,7 +606,7 @@ __device__ __forceinline__ void finishCells(const DenseArgs& a, const T* __restr
                 if (i == specAdj && m == (specSide ? XSet<L>::mask(1) : XSet<L>::mask(0)))
                     xFixUse<L, T, VEC>(std::make_integer_sequence<int, XSet<L>::N>{}, sKeep, specSide, i, f);
                 else
-                    fixCell<L, T, VEC, CH>(cell0 + i, a, m, i, f);
+                    fixCell<L, T, VEC, CH, COH>(cell0 + i, a, m, i, f);
             }
         }
     }
@@ -663,8 +665,11 @@ __host__ __device__ constexpr int stepMinBlocks(int valueRegs) { return valueReg
 
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
 // PEER: the fused step + face push (nlbm_dense_step_push); a separate instantiation so that the plain kernel carries none of it
-template <class COL, typename T, int VEC, bool PEER>
-__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
+// The work of one thread block on one tile (bx, by, bz of the launch grid described above).  COH: every load of the INPUT
+// field is served from L2 (ld.global.cg) and nothing of it is fetched through L1 — for the multi-iteration kernel below,
+// whose input was written by other SMs earlier in the same launch.
+template <class COL, typename T, int VEC, bool PEER, bool COH>
+__device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, const unsigned by, const unsigned bz)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -672,10 +677,10 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     // warps touch the x walls and pay the wall round trip (summary-first mode keeps whole-row warps, LPR = 32)
     const int lane = threadIdx.x;
     const int lpr = 1 << a.lprLog2, tx = lane & (lpr - 1), r = lane >> a.lprLog2;
-    const int seg = blockIdx.x * blockDim.y + threadIdx.y;
-    const int yw = (blockIdx.y * blockDim.z + threadIdx.z) * (32 >> a.lprLog2);
+    const int seg = bx * blockDim.y + threadIdx.y;
+    const int yw = (by * blockDim.z + threadIdx.z) * (32 >> a.lprLog2);
     const int y = yw + r;
-    const int vz = blockIdx.z;
+    const int vz = bz;
     // fused face push: the two boundary planes come first (blockIdx.z 0 -> plane 0, 1 -> plane nz-1, then 1, 2, ...) so
     // that the neighbours have their ghost planes long before they start the next iteration
     const int  zl = PEER ? (vz == 0 ? 0 : (vz == 1 ? a.nzLocal - 1 : vz - 1)) : 0;
@@ -701,7 +706,7 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     const int  specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
     const bool rowsInside = y >= 1 && y + 1 < a.ny && zm >= 1 && zm + 1 < a.nzm;  // every neighbouring row exists
     int        specAdj = -1, specSide = 0;
-    if (VEC > 1 && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {
+    if (VEC > 1 && !COH && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {  // (cp.async goes through L1: not for COH)
         if (x0 == 0)
             specAdj = 1;
         else if (x0 <= a.nx - 2 && a.nx - 2 < x0 + VEC) {
@@ -723,7 +728,7 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     } else
         s = ldPredU2(a.summary + row * a.wpr + (chunk0 >> 5));
     T f[Q][VEC], edge[Q];
-    loadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, tx, lpr, rowOk, f, edge);
+    loadAll<L, T, VEC, COH>(std::make_integer_sequence<int, Q>{}, cell0, a, x0, y, zm, tx, lpr, rowOk, f, edge);
 
     // The two threads of a row that touch the x faces of the box usually own a wall cell next to bulk cells.  Such a thread
     // keeps the wall cell's values of the OUTPUT field through its 16-byte stores (finishCells); fetched after the flags had
@@ -813,18 +818,55 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
     if constexpr (PEER) {
         const int fi = pushes ? face : 0;
         T*        peerDst = (pushes && rowOk) ? reinterpret_cast<T*>(a.peer[fi]) + a.peerOff[fi] + (int64_t)y * a.pitch_y + x0 : nullptr;
-        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi], fi == 0 ? -1 : 1,
-                                 sKeep, specCell, specAdj, specSide);
+        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi],
+                                                                fi == 0 ? -1 : 1, sKeep, specCell, specAdj, specSide);
         if (pushes)
             faceArrive(a, face, lane);
     } else {
-        finishCells<COL, T, VEC>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep, specCell, specAdj, specSide);
+        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep,
+                                                                specCell, specAdj, specSide);
+    }
+}
+
+template <class COL, typename T, int VEC, bool PEER>
+__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
+{
+    stepBody<COL, T, VEC, PEER, false>(a, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// =============================================================== several iterations in ONE launch
+// For boxes of a few hundred thousand cells one iteration lasts ~10 us as a kernel of its own: the launch, the ramp-up of a
+// grid that fills the chip once and the tail cost as much as the work.  k_dense_multi keeps one resident grid (cooperative
+// launch, as many blocks as fit) alive over `iterations` iterations: every block walks the tiles of the step kernel's launch
+// grid with a stride, all blocks meet at a grid-wide barrier, the two fields swap roles, and so on.  While both fields fit the
+// 126 MB L2 (up to ~96^3 D3Q19 fp32) the populations never leave the chip.  Same tile code as k_dense_step (stepBody), with the
+// input field read through L2.  STANDARD view of a partition without neighbours (nothing is exchanged between iterations).
+
+template <class COL, typename T, int VEC>
+__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_multi(DenseArgs a, const MultiArgs m)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const void*    fieldA = a.in;
+    const void*    cacheB = a.keepCache;
+    const unsigned tiles = m.gx * m.gy * m.gz;
+    for (int it = 0; it < m.iterations; ++it) {
+        const bool even = (it & 1) == 0;
+        a.in = even ? fieldA : m.fieldB;
+        a.out = const_cast<void*>(even ? m.fieldB : fieldA);
+        a.keepCache = even ? cacheB : m.keepCacheA;
+        for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const unsigned bx = t % m.gx, by = (t / m.gx) % m.gy, bz = t / (m.gx * m.gy);
+            stepBody<COL, T, VEC, false, true>(a, bx, by, bz);
+        }
+        grid.sync();  // every store of this iteration is visible before anybody reads the field in the next one
     }
 }
 
 // =============================================================== host launcher
-template <class COL, typename T, int VEC, bool PEER = false>
-inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
+// Thread-block and grid shape of the direct kernel for one view (shared by the single-iteration and the multi-iteration launch)
+template <class COL, typename T, int VEC>
+inline void stepGeometry(DenseArgs& a, int nzView, int rowsLog2, int rpwSel, dim3& block, dim3& grid)
 {
     // warp tile: RPW rows x (32 / RPW * VEC) cells.  Measured on B200 (profiles/r01k): whole-row warps are best when rows
     // are long (the SoA planes like long contiguous runs); on short rows every whole-row warp touches an x wall and pays
@@ -851,13 +893,18 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     a.lprLog2 = lprLog2;
     const int rpw = 32 >> lprLog2;
     const int segs = (a.nx + (VEC << lprLog2) - 1) / (VEC << lprLog2);
-    // Block shape: sx warps side by side in x, rows of them stacked in y.  D3Q19 fp32 (16-byte accesses): 4 x 2 — a block then
-    // reads, per population, two contiguous 2 KB stretches instead of eight of 512 bytes, which the DRAM pages like better
+    // Block shape: sx warps side by side in x, rows of them stacked in y.  D3Q19 fp32 (16-byte accesses): up to 4 x 2 — a block
+    // then reads, per population, two contiguous 2 KB stretches instead of eight of 512 bytes, which the DRAM pages like better
     // (measured on B200, profiles/r02f_rows_sweep.log: 512^3 42.28 -> 43.24 GLUPS, 1024x1024x128 42.74 -> 43.16, 256^3 39.2 ->
-    // 41.4, 128^3 30.0 -> 33.7; while the x-wall fix-ups still cost a dependent round trip the stacked shape was the better
-    // one, round 1).  The other lattices / precisions keep the 1 x 8 stack (D3Q27 fp64: 13.93 vs 13.12 GLUPS).
+    // 41.1, 128^3 30.0 -> 33.7; while the x-wall fix-ups still cost a dependent round trip the stacked shape was the better
+    // one, round 1).  Never wider than the row has pieces (64^3: two).  The other lattices / precisions keep the 1 x 8 stack
+    // (D3Q27 fp64: 13.93 vs 13.12 GLUPS).
     int warps = kStepThreads / 32;
-    int sx = (COL::Q == 19 && sizeof(T) == 4 && VEC == 4) ? 4 : 1;
+    int sx = 1;
+    if (COL::Q == 19 && sizeof(T) == 4 && VEC == 4) {
+        while (sx < 4 && 2 * sx <= segs)
+            sx *= 2;
+    }
     int rows = warps / sx;
     if (rowsLog2 > 0) {
         rows = 1 << (rowsLog2 - 1);
@@ -865,15 +912,27 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
             rows = warps;
         sx = warps / rows;
     }
-    dim3 block(32, sx, rows);
-    dim3 grid((segs + sx - 1) / sx, (a.ny + rows * rpw - 1) / (rows * rpw), nzView);
+    block = dim3(32, sx, rows);
+    grid = dim3((segs + sx - 1) / sx, (a.ny + rows * rpw - 1) / (rows * rpw), nzView > 0 ? nzView : 1);
+    a.warpsPerFace = grid.x * grid.y * (unsigned)warps;  // every warp launched for a plane reports in
+}
+// one slot of Q kept values + 2 x |XSet| fix-up operands per thread for the speculative fetches (only x-face threads use theirs)
+template <class COL, typename T, int VEC>
+constexpr size_t stepKeepBytes()
+{
+    return VEC > 1 ? (size_t)(COL::Q + 2 * XSet<Lattice<COL::Q>>::N) * kStepThreads * sizeof(T) : 0;
+}
+
+template <class COL, typename T, int VEC, bool PEER = false>
+inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
+{
+    dim3 block, grid;
+    stepGeometry<COL, T, VEC>(a, nzView, rowsLog2, rpwSel, block, grid);
     if (nzView <= 0)
         return cudaSuccess;
     if (grid.y > 65535)
         return cudaErrorInvalidConfiguration;
-    a.warpsPerFace = grid.x * grid.y * (unsigned)warps;  // every warp launched for a plane reports in
-    // one slot of Q kept values + 2 x |XSet| fix-up operands per thread for the speculative fetches (only x-face threads use theirs)
-    constexpr size_t keepBytes = VEC > 1 ? (size_t)(COL::Q + 2 * XSet<Lattice<COL::Q>>::N) * kStepThreads * sizeof(T) : 0;
+    constexpr size_t keepBytes = stepKeepBytes<COL, T, VEC>();
     if constexpr (keepBytes > 48 * 1024) {
         static bool raised[64] = {};  // per instantiation and device; racing host threads set the same value
         int         dev = 0;
@@ -888,6 +947,39 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     }
     k_dense_step<COL, T, VEC, PEER><<<grid, block, keepBytes, st>>>(a);
     return cudaGetLastError();
+}
+
+// `iterations` iterations in one cooperative launch (k_dense_multi); a.in / m.fieldB are the two fields
+template <class COL, typename T, int VEC>
+inline cudaError_t launchMultiVec(DenseArgs a, MultiArgs m, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
+{
+    dim3 block, grid;
+    stepGeometry<COL, T, VEC>(a, nzView, rowsLog2, rpwSel, block, grid);
+    if (nzView <= 0 || m.iterations <= 0)
+        return cudaSuccess;
+    a.specXFix = 0;  // those operands change every iteration and cp.async fetches through L1
+    m.gx = grid.x;
+    m.gy = grid.y;
+    m.gz = grid.z;
+    constexpr size_t keepBytes = stepKeepBytes<COL, T, VEC>();
+    int              dev = 0, sms = 0, perSm = 0;
+    cudaError_t      e = cudaGetDevice(&dev);
+    if (e == cudaSuccess)
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess && keepBytes > 48 * 1024)
+        e = cudaFuncSetAttribute(k_dense_multi<COL, T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)keepBytes);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_dense_multi<COL, T, VEC>, kStepThreads, keepBytes);
+    if (e != cudaSuccess)
+        return e;
+    if (perSm < 1)
+        return cudaErrorLaunchOutOfResources;
+    const unsigned long long tiles = (unsigned long long)grid.x * grid.y * grid.z;
+    unsigned                 blocks = (unsigned)sms * (unsigned)perSm;
+    if (blocks > tiles)
+        blocks = (unsigned)tiles;
+    void* args[] = {&a, &m};
+    return cudaLaunchCooperativeKernel((const void*)k_dense_multi<COL, T, VEC>, dim3(blocks), block, args, keepBytes, st);
 }
 
 template <class COL, typename T>
@@ -915,6 +1007,26 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
     if (vec >= 2)
         return launchStepVec<COL, T, 2>(a, nzView, rowsLog2, rpwSel, st);
     return launchStepVec<COL, T, 1>(a, nzView, rowsLog2, rpwSel, st);
+}
+
+template <class COL, typename T>
+inline cudaError_t launchMulti(const DenseArgs& a, const MultiArgs& m, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
+{
+    constexpr int maxVec = 16 / (int)sizeof(T);
+    if (vec <= 0 || vec > maxVec) {
+        vec = maxVec;
+        while (vec > 1 && COL::Q * vec * (int)sizeof(T) / 4 > 80)
+            vec >>= 1;
+    }
+    while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
+        vec >>= 1;
+    if constexpr (maxVec >= 4) {
+        if (vec == 4)
+            return launchMultiVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
+    }
+    if (vec >= 2)
+        return launchMultiVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
+    return launchMultiVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
 }
 
 }  // namespace nlbm

@@ -31,6 +31,23 @@ cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, const StepLaunch& 
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launchMultiFast(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st)
+{
+    switch (kind) {
+        case kD3Q19_F32:
+            return launchMulti<CollideD3Q19Fast<float, 1>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q19_F64:
+            return launchMulti<CollideD3Q19Fast<double, 1>, double>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q19_F32C64:
+            return launchMulti<CollideD3Q19Ref<float, double, 1>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q27_F32:
+            return launchMulti<CollideD3Q27Fast<float, 1>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q27_F64:
+            return launchMulti<CollideD3Q27Fast<double, 1>, double>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 void tmaTileShape(int elemBytes, int nx, int* tx, int* ty)
 {
     int l2;

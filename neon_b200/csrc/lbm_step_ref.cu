@@ -32,6 +32,25 @@ cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, const StepLaunch& l
     }
     return cudaErrorInvalidValue;
 }
+cudaError_t launchMultiRef(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st)
+{
+    switch (kind) {
+        case kD3Q19_F32:
+            if (l.exact)
+                return launchMulti<CollideD3Q19Exact<0>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+            return launchMulti<CollideD3Q19Ref<float, float, 0>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q19_F64:
+            return launchMulti<CollideD3Q19Ref<double, double, 0>, double>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q19_F32C64:
+            return launchMulti<CollideD3Q19Ref<float, double, 0>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q27_F32:
+            return launchMulti<CollideD3Q27Ref<float, 0>, float>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+        case kD3Q27_F64:
+            return launchMulti<CollideD3Q27Ref<double, 0>, double>(a, m, l.nzView, l.vec, l.rowsLog2, l.rpwSel, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 // ---------------------------------------------------------------- self-test of the exact building blocks (tests/)
 // kind 0: exact::widenPos(f) against the conversion instruction for EVERY positive normal float (n and seed ignored);
 // kind 1: exact::div3 against IEEE division on n pseudo-random (a0, a1, a2, b) inside div3's guard, zero numerators included.

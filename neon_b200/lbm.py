@@ -116,6 +116,7 @@ class LbmIteration:
                  pipelined: bool = True):
         self.pop = [fInField, fOutField]
         self.flag, self.omega, self.parity = flagField, omega, 0
+        self._step_args = (lattice_q, compute, int(arith) | int(opts))
         bk = fInField.grid.backend
         self.lbmTwoPop = []
         self.fused = None
@@ -141,6 +142,28 @@ class LbmIteration:
         else:
             self.lbmTwoPop[self.parity].run()
         self.parity ^= 1
+
+    _KINDS = {(19, "float32", "float32"): 0, (19, "float64", "float64"): 1, (19, "float32", "float64"): 2,
+              (27, "float32", "float32"): 3, (27, "float64", "float64"): 4}
+
+    def runMany(self, iterations: int) -> None:
+        """``iterations`` iterations with ONE kernel launch (nlbm_dense_step_n: a resident grid that meets at a grid-wide barrier
+        between iterations) when the field lives on one device as a dense partition — the regime of small boxes, where an
+        iteration lasts ~10 us as a kernel of its own.  Anything else (several partitions, bGrid) runs ``iterations`` x run()."""
+        f = self.pop[self.parity]
+        g = f.grid
+        bk = g.backend
+        q, compute, o = self._step_args
+        if (iterations < 1 or bk.world > 1 or bk.runtime != Runtime.stream or self.fused is not None or getattr(g, "kind", "dense") != "dense"
+                or g.z_halo != 0):
+            for _ in range(iterations):
+                self.run()
+            return
+        fin, fout = self.pop[self.parity], self.pop[self.parity ^ 1]
+        kind = self._KINDS[(q, str(fin.dtype), str(fin.dtype if compute is None else np.dtype(compute)))]
+        desc = g.desc(fin, fout, self.flag)
+        capi.call("nlbm_dense_step_n", kind, C.byref(desc), fin.wallCachePtr(), self.omega, iterations, o, bk.streamHandle(0))
+        self.parity ^= iterations & 1
 
     def runGraph(self, iterations: int) -> int:
         """ONE device: ``iterations`` (rounded up to an even count, so that the field parity is back where it started)

@@ -273,17 +273,19 @@ def test_generic_container_app_builds_with_the_generic_kernel(app):
     """Grid::newContainer(name, loadingLambda) instantiates the generic span kernel for every user lambda (nvcc)"""
     assert os.path.exists(GEN)
     sass = subprocess.run(["cuobjdump", "-sass", GEN], capture_output=True, text=True).stdout
-    assert sass.count("neonLambdaOnSpan") >= 3 and "sm_100a" in sass
+    assert sass.count("neonLambdaOnSpan") >= 3 and sass.count("neonLambdaOnBlocks") >= 2 and "sm_100a" in sass
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("devices", [(0,), (0, 0), (0, 0, 0, 0), (0, 1)])
 def test_generic_lambda_containers(app, tmp_path, devices):
-    """user-written MAP / STENCIL / LBM device lambdas through newContainer + Skeleton (OCC, halo updates) on 1-4 partitions"""
+    """user-written MAP / STENCIL / LBM device lambdas through dGrid::newContainer and bGrid::newContainer + Skeleton (every
+    Occ, both transfer modes, halo updates; a map -> stencil -> map sequence in one Skeleton) on 1-4 partitions"""
     torch = pytest.importorskip("torch")
     if max(devices) >= torch.cuda.device_count():
         pytest.skip("needs two GPUs")
     r = subprocess.run([GEN, "--deviceIds", *[str(d) for d in devices], "--n", "36"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith(("PASS", "FAIL"))]
-    assert len(lines) == 7 and all(l.startswith("PASS") for l in lines), r.stdout
+    # 2 axpy (dGrid, sparse bGrid) + 4 Occ x (2 modes x 2 grids diffusion + sequence + LBM)
+    assert len(lines) == 2 + 4 * (4 + 1 + 1) and all(l.startswith("PASS") for l in lines), r.stdout

@@ -201,6 +201,37 @@ def test_reference_bits_outside_the_guard_of_the_lean_evaluation(nb, bk, oracle,
     assert np.array_equal(it.getInput().updateHostData().view(np.uint8), ref.view(np.uint8))
 
 
+@pytest.mark.parametrize("q,store,dim,geom,iters", [(19, np.float32, (40, 24, 20), 1, 7), (19, np.float32, (64, 64, 64), 0, 12), (27, np.float64, (34, 18, 14), 1, 5),
+                                                    (19, np.float64, (33, 17, 12), 2, 6), (27, np.float32, (70, 20, 24), 1, 4),
+                                                    (19, np.float32, (300, 40, 30), 1, 3)])
+def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, iters):
+    """nlbm_dense_step_n (LbmIteration.runMany): a resident grid iterates with a grid-wide barrier between iterations, reading
+    the field the previous iteration wrote through L2.  Same bits as the oracle in REFERENCE arithmetic, the same bits as
+    iteration-by-iteration launches in FAST arithmetic, odd and even iteration counts (where the result lands), more tiles than
+    resident blocks (300 x 40 x 30) and fewer."""
+    from neon_b200 import problems as P
+    nx, ny, nz = dim
+    cls = oracle.classify(geom, nx, ny, nz)
+    mask = oracle.wall_mask(q, cls)
+    pop = oracle.init_pop(q, cls, store)
+    omega = oracle.omega_cavity(max(dim))
+    ref = oracle.run(q, pop, cls, mask, omega, iters + 1)
+    for arith in (nb.ARITH_REFERENCE, nb.ARITH_FAST):
+        grid = nb.dGrid(bk, dim)
+        pop0, pop1, flag = P.setup_host(grid, q, store, cls, pop)
+        it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q, arith=arith)
+        it.runMany(iters)       # one launch
+        it.runMany(1)           # and one more through the same entry point: parity bookkeeping
+        bk.syncAll()
+        many = it.getInput().updateHostData()
+        if arith == nb.ARITH_REFERENCE:
+            assert np.array_equal(many.view(np.uint8), ref.view(np.uint8))
+        else:
+            one, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters + 1, nb.ARITH_FAST)
+            assert np.array_equal(many.view(np.uint8), one.view(np.uint8))
+        assert np.array_equal(flag.masks(), mask)
+
+
 def test_device_setup_matches_oracle(nb, bk, oracle):
     """nlbm_dense_classify / wall_mask / init_pop against the oracle, bit for bit, all geometries."""
     from neon_b200 import problems as P

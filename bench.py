@@ -67,9 +67,9 @@ def parse():
                          "speculative x-face fix-up operands, 1<<30 literal transcription in REFERENCE arithmetic); never changes results")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: halo update in front of the consumer instead of pushed after BOUNDARY")
     ap.add_argument("--graph-iters", type=int, default=-1,
-                    help="one device: iterations per host call — one multi-iteration launch, or a CUDA-graph replay with --no-persistent "
+                    help="one device: iterations per host call — a CUDA-graph replay, or one multi-iteration launch with --persistent "
                          "(0 = plain launches; default: 0 for boxes above 2^22 cells, else 10)")
-    ap.add_argument("--no-persistent", action="store_true", help="small boxes: CUDA-graph replay of single-iteration launches instead of the multi-iteration kernel")
+    ap.add_argument("--persistent", action="store_true", help="small boxes: the multi-iteration kernel (nlbm_dense_step_n) instead of a CUDA-graph replay of single-iteration launches (measured slower, DESIGN.md §3.3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline line only: no arith_reference, no extra_configs")
@@ -340,7 +340,7 @@ class Job:
         main_stream = bk.stream(0)
         per_call = 1
         runner = it.run
-        if graph_iters > 1 and not is_block and not args.no_persistent:
+        if graph_iters > 1 and not is_block and args.persistent:
             per_call = graph_iters + (graph_iters & 1)  # LbmIteration.runMany: G iterations in one cooperative launch
 
             def runner():
@@ -376,7 +376,7 @@ class Job:
         nnb = (dn is not None) + (up is not None)
         pipelined = self.world > 1 and not args.no_pipeline and args.transport in ("auto", "ipc") and occ != nb.Occ.none
         if self.world == 1:
-            launches_step = 1.0 / per_call if (graph_iters > 1 and not is_block and not args.no_persistent) else 1
+            launches_step = 1.0 / per_call if (graph_iters > 1 and not is_block and args.persistent) else 1
         elif args.transport == "fused":
             launches_step = 1 + nnb  # step+push kernel, one flag wait per neighbour
         elif pipelined:
@@ -418,7 +418,7 @@ class Job:
                "dtype": "f32" if dtype.itemsize == 4 else "f64", "arith": arith_name, "dim": list(dim), "lattice": f"D3Q{q}",
                "grid": "bGrid" if is_block else "dGrid", "roofline": roofline, "gpu_launches": int(round(launches_step * steps)),
                "graph_iters": per_call if graph_iters > 1 else 0,
-               "iterations_per_launch": per_call if (graph_iters > 1 and not is_block and not args.no_persistent) else 1, "l2": l2_note, "clocks": clocks,
+               "iterations_per_launch": per_call if (graph_iters > 1 and not is_block and args.persistent) else 1, "l2": l2_note, "clocks": clocks,
                "partition": ((f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes")
                              if self.world > 1 else "single partition")}
         del it, runner

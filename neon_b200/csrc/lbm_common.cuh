@@ -143,6 +143,7 @@ struct MultiArgs
     const void* keepCacheA;  // x-face cache of a.in (a.keepCache is a.out's, i.e. fieldB's); may be null like a.keepCache
     int32_t     iterations;
     uint32_t    gx, gy, gz;  // the step kernel's launch grid: tiles to walk
+    unsigned*   barrier;     // arrival counter of the grid-wide barrier (zero at launch)
 };
 
 // ---------------------------------------------------------------- vector access
@@ -224,46 +225,43 @@ __device__ __forceinline__ double ldPred1(const double* p, bool pred)
     ldPred(p, pred, v);
     return v[0];
 }
-// The same loads served from L2 (ld.global.cg): for the multi-iteration kernel, where the field a thread reads was written
-// by other SMs earlier in the SAME launch — the non-coherent path (and L1) may still hold the values of two iterations ago.
+// The same loads as ordinary (coherent) global loads: for the multi-iteration kernel, where the field a thread reads was
+// written by other SMs earlier in the SAME launch.  ld.global.nc is undefined for data written during the kernel; an ordinary
+// load is ordered by the grid-wide barrier between iterations (which also invalidates L1).  (ld.global.cg compiles to
+// LDG.STRONG.GPU on sm_100a and halved the throughput of the tile loop: profiles/r02j_small_sweep.log.)
 __device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[4])
 {
     asm volatile(
         "{\n.reg .pred q;\nsetp.ne.u32 q, %5, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\nmov.f32 %2, 0f00000000;\n"
-        "mov.f32 %3, 0f00000000;\n@q ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n}\n"
+        "mov.f32 %3, 0f00000000;\n@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n}\n"
         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
-        : "l"(p), "r"((uint32_t)pred)
-        : "memory");
+        : "l"(p), "r"((uint32_t)pred));
 }
 __device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[2])
 {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f32 %0, 0f00000000;\nmov.f32 %1, 0f00000000;\n"
-                 "@q ld.global.cg.v2.f32 {%0, %1}, [%2];\n}\n"
+                 "@q ld.global.v2.f32 {%0, %1}, [%2];\n}\n"
                  : "=f"(v[0]), "=f"(v[1])
-                 : "l"(p), "r"((uint32_t)pred)
-                 : "memory");
+                 : "l"(p), "r"((uint32_t)pred));
 }
 __device__ __forceinline__ void ldPredCg(const float* p, bool pred, float (&v)[1])
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f32 %0, 0f00000000;\n@q ld.global.cg.f32 %0, [%1];\n}\n"
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f32 %0, 0f00000000;\n@q ld.global.f32 %0, [%1];\n}\n"
                  : "=f"(v[0])
-                 : "l"(p), "r"((uint32_t)pred)
-                 : "memory");
+                 : "l"(p), "r"((uint32_t)pred));
 }
 __device__ __forceinline__ void ldPredCg(const double* p, bool pred, double (&v)[2])
 {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %3, 0;\nmov.f64 %0, 0d0000000000000000;\nmov.f64 %1, 0d0000000000000000;\n"
-                 "@q ld.global.cg.v2.f64 {%0, %1}, [%2];\n}\n"
+                 "@q ld.global.v2.f64 {%0, %1}, [%2];\n}\n"
                  : "=d"(v[0]), "=d"(v[1])
-                 : "l"(p), "r"((uint32_t)pred)
-                 : "memory");
+                 : "l"(p), "r"((uint32_t)pred));
 }
 __device__ __forceinline__ void ldPredCg(const double* p, bool pred, double (&v)[1])
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.cg.f64 %0, [%1];\n}\n"
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.f64 %0, 0d0000000000000000;\n@q ld.global.f64 %0, [%1];\n}\n"
                  : "=d"(v[0])
-                 : "l"(p), "r"((uint32_t)pred)
-                 : "memory");
+                 : "l"(p), "r"((uint32_t)pred));
 }
 template <bool COH, typename T, int N>
 __device__ __forceinline__ void ldPredSel(const T* p, bool pred, T (&v)[N])
@@ -305,12 +303,12 @@ __device__ __forceinline__ double ldPredKeepNc1(const double* p, bool pred, doub
 }
 __device__ __forceinline__ float ldPredKeepCg1(const float* p, bool pred, float keep)
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.cg.f32 %0, [%1];\n}\n" : "+f"(keep) : "l"(p), "r"((uint32_t)pred) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f32 %0, [%1];\n}\n" : "+f"(keep) : "l"(p), "r"((uint32_t)pred));
     return keep;
 }
 __device__ __forceinline__ double ldPredKeepCg1(const double* p, bool pred, double keep)
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.cg.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.global.f64 %0, [%1];\n}\n" : "+d"(keep) : "l"(p), "r"((uint32_t)pred));
     return keep;
 }
 template <bool COH, typename T>

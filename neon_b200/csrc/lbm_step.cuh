@@ -17,8 +17,7 @@
 //    per-cell fix-up executed only by cells whose wallNghBitflag is non-zero.
 //  * results leave through 16-byte streaming stores; non-bulk cells are never written (LbmTools.h:304).
 #pragma once
-#include <cooperative_groups.h>
-
+#include <mutex>
 #include <type_traits>
 #include <utility>
 
@@ -666,10 +665,11 @@ __host__ __device__ constexpr int stepMinBlocks(int valueRegs) { return valueReg
 // grid  = (ceil(segments/blockDim.y), ceil(ny/blockDim.z), planes of the view), block = (32, SEGS, ROWS)
 // PEER: the fused step + face push (nlbm_dense_step_push); a separate instantiation so that the plain kernel carries none of it
 // The work of one thread block on one tile (bx, by, bz of the launch grid described above).  COH: every load of the INPUT
-// field is served from L2 (ld.global.cg) and nothing of it is fetched through L1 — for the multi-iteration kernel below,
-// whose input was written by other SMs earlier in the same launch.
+// field is an ordinary coherent load (no ld.global.nc, no cp.async prefetch of values that change) — for the multi-iteration
+// kernel below, whose input was written by other SMs earlier in the same launch.
 template <class COL, typename T, int VEC, bool PEER, bool COH>
-__device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, const unsigned by, const unsigned bz)
+__device__ __forceinline__ void stepBody(const DenseArgs& a, const void* __restrict__ fieldIn, void* __restrict__ fieldOut, const void* keepCache,
+                                         const unsigned bx, const unsigned by, const unsigned bz)
 {
     constexpr int Q = COL::Q;
     using L = Lattice<Q>;
@@ -698,7 +698,7 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, 
     const int     chunk0 = seg * VEC;  // summary-first mode: the warp's VEC chunks lie in one summary word (VEC divides 32)
     const int     x0 = xw + tx * VEC;
     const int64_t cellOff = (int64_t)zm * a.pitch_z + (int64_t)y * a.pitch_y + x0;
-    const T*      cell0 = reinterpret_cast<const T*>(a.in) + cellOff;
+    const T*      cell0 = reinterpret_cast<const T*>(fieldIn) + cellOff;
 
     // x-face threads: the thread that owns the wall cell at x = 0 / x = nx-1 next to bulk cells (specCell = its index), and
     // the bulk cell next to it (specAdj, side)
@@ -742,11 +742,11 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, 
     if (specCell >= 0) {
         // from the field's x-face cache when the caller maintains one (y-contiguous: no isolated DRAM row activations),
         // else from the wall cell's own rows
-        const T*      w = reinterpret_cast<const T*>(a.out) + cellOff + specCell;
+        const T*      w = reinterpret_cast<const T*>(fieldOut) + cellOff + specCell;
         int64_t       stride = a.pitch_q;
-        if (a.keepCache != nullptr) {
+        if (keepCache != nullptr) {
             stride = (int64_t)a.nzm * a.ny;
-            w = reinterpret_cast<const T*>(a.keepCache) + (x0 == 0 ? 0 : Q * stride) + (int64_t)zm * a.ny + y;
+            w = reinterpret_cast<const T*>(keepCache) + (x0 == 0 ? 0 : Q * stride) + (int64_t)zm * a.ny + y;
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -818,12 +818,12 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, 
     if constexpr (PEER) {
         const int fi = pushes ? face : 0;
         T*        peerDst = (pushes && rowOk) ? reinterpret_cast<T*>(a.peer[fi]) + a.peerOff[fi] + (int64_t)y * a.pitch_y + x0 : nullptr;
-        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi],
+        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(fieldOut) + cellOff, fl, special, f, peerDst, a.peerPitchQ[fi],
                                                                 fi == 0 ? -1 : 1, sKeep, specCell, specAdj, specSide);
         if (pushes)
             faceArrive(a, face, lane);
     } else {
-        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(a.out) + cellOff, fl, special, f, nullptr, 0, 0, sKeep,
+        finishCells<COL, T, VEC, (sizeof(T) == 4 ? 9 : 5), COH>(a, cell0, reinterpret_cast<T*>(fieldOut) + cellOff, fl, special, f, nullptr, 0, 0, sKeep,
                                                                 specCell, specAdj, specSide);
     }
 }
@@ -831,7 +831,7 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const unsigned bx, 
 template <class COL, typename T, int VEC, bool PEER>
 __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
 {
-    stepBody<COL, T, VEC, PEER, false>(a, blockIdx.x, blockIdx.y, blockIdx.z);
+    stepBody<COL, T, VEC, PEER, false>(a, a.in, a.out, a.keepCache, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // =============================================================== several iterations in ONE launch
@@ -842,28 +842,49 @@ __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (in
 // 126 MB L2 (up to ~96^3 D3Q19 fp32) the populations never leave the chip.  Same tile code as k_dense_step (stepBody), with the
 // input field read through L2.  STANDARD view of a partition without neighbours (nothing is exchanged between iterations).
 
-template <class COL, typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_multi(DenseArgs a, const MultiArgs m)
+// Grid-wide barrier of the multi-iteration kernel.  cooperative_groups' grid.sync() spins on an ACQUIRE load, which on sm_100a
+// invalidates the SM's L1 on every spin (ncu r02k: CCTL.IVALL executed 800 000 times in ten iterations of a 64^3 box) — also for
+// the co-resident block that is still computing.  Here one thread per block announces its arrival (release), spins on a RELAXED
+// load with a back-off, and the block passes ONE acquire fence afterwards.  `counter` counts arrivals since the launch: the
+// barrier after iteration t is open once it reaches (t + 1) * gridDim.x.
+__device__ __forceinline__ void gridBarrier(unsigned* counter, const unsigned target)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const void*    fieldA = a.in;
-    const void*    cacheB = a.keepCache;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        unsigned seen;
+        asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
+        ++seen;
+        while (seen < target) {
+            __nanosleep(64);
+            asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// One block per SM and no register cap: the tile loop keeps a dozen values alive across the tile code, and at the 128
+// registers of the step kernel they spill — which costs an L2 round trip each here, because every barrier invalidates L1.
+template <class COL, typename T, int VEC>
+__global__ void __launch_bounds__(kStepThreads, 1) k_dense_multi(const DenseArgs a, const MultiArgs m)
+{
     const unsigned tiles = m.gx * m.gy * m.gz;
     for (int it = 0; it < m.iterations; ++it) {
-        const bool even = (it & 1) == 0;
-        a.in = even ? fieldA : m.fieldB;
-        a.out = const_cast<void*>(even ? m.fieldB : fieldA);
-        a.keepCache = even ? cacheB : m.keepCacheA;
+        // the kernel arguments stay where they are (constant bank); only the three pointers that swap are selected here
+        const bool  even = (it & 1) == 0;
+        const void* fin = even ? a.in : m.fieldB;
+        void*       fout = const_cast<void*>(even ? m.fieldB : a.in);
+        const void* keep = even ? a.keepCache : m.keepCacheA;
         for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
             const unsigned bx = t % m.gx, by = (t / m.gx) % m.gy, bz = t / (m.gx * m.gy);
-            stepBody<COL, T, VEC, false, true>(a, bx, by, bz);
+            stepBody<COL, T, VEC, false, true>(a, fin, fout, keep, bx, by, bz);
         }
-        grid.sync();  // every store of this iteration is visible before anybody reads the field in the next one
+        // every store of this iteration is visible before anybody reads the field in the next one
+        if (it + 1 < m.iterations)
+            gridBarrier(m.barrier, (unsigned)(it + 1) * gridDim.x);
     }
 }
 
-// =============================================================== host launcher
 // Thread-block and grid shape of the direct kernel for one view (shared by the single-iteration and the multi-iteration launch)
 template <class COL, typename T, int VEC>
 inline void stepGeometry(DenseArgs& a, int nzView, int rowsLog2, int rpwSel, dim3& block, dim3& grid)
@@ -949,6 +970,21 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     return cudaGetLastError();
 }
 
+// Arrival counters of the multi-iteration kernel's barrier: 64 words per device, handed out round-robin (a launch owns its word
+// until 63 later launches on the same device have been issued), allocated on first use and kept for the life of the process.
+inline unsigned* multiBarrierWord(int dev)
+{
+    static std::mutex mu;
+    static unsigned*  ring[64] = {};
+    static unsigned   next[64] = {};
+    if (dev < 0 || dev >= 64)
+        return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ring[dev] == nullptr && cudaMalloc(reinterpret_cast<void**>(&ring[dev]), 64 * sizeof(unsigned)) != cudaSuccess)
+        return nullptr;
+    return ring[dev] + (next[dev]++ & 63u);
+}
+
 // `iterations` iterations in one cooperative launch (k_dense_multi); a.in / m.fieldB are the two fields
 template <class COL, typename T, int VEC>
 inline cudaError_t launchMultiVec(DenseArgs a, MultiArgs m, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
@@ -978,7 +1014,15 @@ inline cudaError_t launchMultiVec(DenseArgs a, MultiArgs m, int nzView, int rows
     unsigned                 blocks = (unsigned)sms * (unsigned)perSm;
     if (blocks > tiles)
         blocks = (unsigned)tiles;
+    // arrival counter of the grid-wide barrier: one word of a small per-device ring, zeroed in stream order before the launch
+    m.barrier = multiBarrierWord(dev);
+    if (m.barrier == nullptr)
+        return cudaErrorMemoryAllocation;
+    e = cudaMemsetAsync(m.barrier, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess)
+        return e;
     void* args[] = {&a, &m};
+    // cooperative launch: the runtime guarantees that all blocks are resident, which the barrier needs
     return cudaLaunchCooperativeKernel((const void*)k_dense_multi<COL, T, VEC>, dim3(blocks), block, args, keepBytes, st);
 }
 
@@ -991,6 +1035,11 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
         vec = maxVec;
         while (vec > 1 && COL::Q * vec * (int)sizeof(T) / 4 > 80)
             vec >>= 1;
+        // boxes of up to ~one chip-load of cells (a 96^3 box is 3 waves) are bound by the latency of ONE thread's chain of
+        // loads, collisions and stores, not by bandwidth: half as many cells per thread, three blocks per SM
+        // (profiles/r02i_small_sweep.log: 64^3 22.1 -> 23.4 GLUPS, 96^3 25.4 -> 27.3; 128^3 is better off with 16 bytes)
+        if (!a.peerMode && vec == 4 && (int64_t)a.nx * a.ny * nzView <= (int64_t)1 << 20)
+            vec = 2;
     }
     while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
         vec >>= 1;

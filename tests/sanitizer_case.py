@@ -1,6 +1,7 @@
 """Small run of every kernel family, meant to be executed under compute-sanitizer (tests/test_gpu_sanitizer.py):
-dense D3Q19 fp32 (vector width 4, x-face cache, wall fix-ups, REFERENCE and FAST arithmetic), dense D3Q27 fp64, the
-TMA-fed variant, bGrid, set-up / rho-u kernels, and a 3-partition halo update on one device."""
+dense D3Q19 fp32 (vector width 4, x-face cache, wall fix-ups, REFERENCE and FAST arithmetic, the multi-iteration kernel, the
+plain path of the REFERENCE evaluation), dense D3Q27 fp64, the TMA-fed variant, bGrid, set-up / rho-u kernels, and a
+3-partition halo update on one device."""
 import os
 import sys
 
@@ -26,8 +27,18 @@ def main():
                              opts=opts)
         for _ in range(3):
             it.run()
+        if not opts:
+            it.runMany(3)  # several iterations in one cooperative launch (grid-wide barrier, coherent loads)
         bk.syncAll()
         assert np.isfinite(it.getInput().updateHostData()).all()
+    # REFERENCE arithmetic on a lid far outside the guard of its lean evaluation: fast and plain path inside the same warps
+    grid = nb.dGrid(bk, (40, 12, 10))
+    cls = P.host_classes(P.CAVITY_SPHERE, (40, 12, 10))
+    pop0, pop1, flag = P.setup_host(grid, 19, np.float32, cls, P.host_populations(19, cls, np.float32, 0.4))
+    it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, 1.1, arith=nb.ARITH_REFERENCE)
+    for _ in range(4):
+        it.run()
+    bk.syncAll()
     # rho / u
     grid = nb.dGrid(bk, (24, 12, 10))
     pop0, pop1, flag = P.setup_device(grid, 19, np.float32, P.CAVITY)

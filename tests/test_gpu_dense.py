@@ -103,8 +103,9 @@ def test_parity_with_oracle(nb, bk, oracle, q, store, compute, dim, geom, iters)
         assert np.array_equal(out.view(np.uint8), ref.view(np.uint8)), f"REFERENCE arithmetic must be bit-exact (kernel {kern})"
         fast, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_FAST, compute, opts=nb.opt_kernel(kern))
         assert rel_err(fast, ref) < REL_TOL[np.dtype(store)]
-    # every vector width of the direct kernel computes the same bits
-    for vec in (1, 2):
+    # every vector width of the direct kernel computes the same bits (the default is 2 cells per thread for views of up to
+    # 2^20 cells and 4 above: small boxes would otherwise never run the 16-byte path)
+    for vec in (1, 2, 4):
         v, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters, nb.ARITH_REFERENCE, compute,
                         opts=nb.opt_vec(vec) | nb.opt_kernel(nb.KERNEL_DIRECT))
         assert np.array_equal(v.view(np.uint8), ref.view(np.uint8)), f"vec={vec}"

@@ -86,6 +86,10 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
  * 1 128 B, 2 64 B, 3 none), bits 18..19 consumer groups per CTA (0 = default 3).                            */
 #define NLBM_OPT_TMA_L2PROMO(p) (((p)&0x3) << 16)
 #define NLBM_OPT_TMA_GROUPS(g) (((g)&0x3) << 18)
+/* the same bits 16..19 in nlbm_dense_step_n (launch chain; never changes results): how many z planes of an iteration start on the
+ * per-plane counters instead of waiting for the whole previous launch — 0 library default (one chip-load of blocks), 1..14:
+ * 2^(e-1) planes, 15: every plane.                                                                              */
+#define NLBM_OPT_CHAIN_EARLY(e) (((e)&0xF) << 16)
 /* bit 20 (direct kernel): consult the row summary first and fetch flag words only where a 32-cell chunk holds a non-plain
  * cell (saves up to 4 B/cell of traffic).  Default (bit clear): the flag words travel with the populations — one dependent
  * memory round trip less for warps that touch walls, measured faster on B200.                                          */
@@ -113,6 +117,7 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2
+#define NLBM_KERNEL_COOPERATIVE 3 /* nlbm_dense_step_n only: one resident grid + grid-wide barrier instead of the launch chain */
 
 /* Dense (dGrid) partition descriptor: one z-slab of the global box on one GPU.
  * Replaces what the reference kernel receives by value: dSpan {dataView, zHalo,
@@ -226,15 +231,18 @@ typedef struct nlbm_peer_desc {
     uint32_t* counters;      /* 2 words of THIS device's memory, zero before the first call, owned by the caller */
     uint32_t  value;
 } nlbm_peer_desc;
-/* ---- several iterations in ONE launch (small boxes) ---------------------------------------------------------------------
- * `iterations` LBM iterations of a partition WITHOUT neighbours (d->z_halo == 0) in one cooperative launch: iteration t reads
- * d->pop_in when t is even, else d->pop_out, and writes the other field — the two-field scheme of LbmIteration.h:56-61 without
- * returning to the host (or to the stream) in between.  The result is in pop_out when `iterations` is odd, else in pop_in.
- * d->wall_cache is pop_out's x-face cache as in a step call, wall_cache_in the one of pop_in (both may be NULL).  kind as in
- * nlbm_dense_step_push (0 d3q19_f32 ... 4 d3q27_f64).  A box of a few hundred thousand cells iterates in ~10 us as a kernel of its
- * own — launch, ramp-up and tail cost as much as the work; here one resident grid walks the tiles and meets at a grid-wide
- * barrier between iterations, and while both fields fit the L2 the populations never leave the chip.  Same results as
- * `iterations` step calls, bit for bit.                                                                                    */
+/* ---- several iterations without returning to the stream (small boxes) ----------------------------------------------------
+ * `iterations` LBM iterations of a partition WITHOUT neighbours (d->z_halo == 0): iteration t reads d->pop_in when t is even,
+ * else d->pop_out, and writes the other field — the two-field scheme of LbmIteration.h:56-61 without returning to the host (or to
+ * the stream) in between.  The result is in pop_out when `iterations` is odd, else in pop_in.  d->wall_cache is pop_out's x-face
+ * cache as in a step call, wall_cache_in the one of pop_in (both may be NULL).  kind as in nlbm_dense_step_push (0 d3q19_f32 ...
+ * 4 d3q27_f64).  A box of a few hundred thousand cells iterates in ~10 us as a kernel of its own — launch, ramp-up and tail cost
+ * as much as the work.  Default: a CHAIN of dependent launches (programmatic dependent launch, one per iteration): iteration t+1
+ * is launched while t still runs, and a tile of plane z starts as soon as planes z-1, z, z+1 of the previous iteration are
+ * complete (per-plane counters in device memory) — no grid ever waits for a whole grid, so launch gap, ramp-up and tail of
+ * consecutive iterations overlap.  NLBM_OPT_KERNEL(NLBM_KERNEL_COOPERATIVE): one resident grid (cooperative launch) that walks
+ * the tiles and meets at a grid-wide barrier between iterations (measured slower; also used when the view has more than 4096
+ * planes).  Same results as `iterations` step calls, bit for bit.  Capturable into a CUDA graph.                              */
 int nlbm_dense_step_n(int kind, const nlbm_dense_desc* d, const void* wall_cache_in, double omega, int iterations, int opts, void* stream);
 
 int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream);

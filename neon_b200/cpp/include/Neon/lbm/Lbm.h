@@ -350,6 +350,8 @@ struct LbmIterationT
     {
         pop[0] = fIn;
         pop[1] = fOut;
+        flag = cellTypeField;
+        mOmega = static_cast<double>(omega);
         for (int target = 0; target < 2; ++target) {
             std::vector<Neon::set::Container> ops;
             ops.push_back(LbmTools::iteration(stencilSemantic, pop[target], cellTypeField, omega, pop[1 - target]));
@@ -364,12 +366,55 @@ struct LbmIterationT
         lbmTwoPop[parity].run();
         parity = 1 - parity;
     }
+    /* `n` iterations with ONE library call (nlbm_dense_step_n) when the field is a single dense partition: a chain of
+     * dependent launches whose tiles wait plane-wise for the previous iteration, so that launch gap, ramp-up and tail of
+     * consecutive iterations overlap (small boxes).  Anything else runs n x run(). */
+    auto runMany(int n) -> void
+    {
+        constexpr bool isBlock = std::is_same_v<typename PopulationField::Grid, Neon::bGrid>;
+        if constexpr (!isBlock) {
+            constexpr bool f32 = std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, float>;
+            constexpr bool f64 = std::is_same_v<LbmStoreType, double> && std::is_same_v<LbmComputeType, double>;
+            constexpr bool f32c64 = std::is_same_v<LbmStoreType, float> && std::is_same_v<LbmComputeType, double>;
+            constexpr int  kind = Lattice::Q == 19 ? (f32 ? 0 : (f64 ? 1 : (f32c64 ? 2 : -1))) : (f32 ? 3 : (f64 ? 4 : -1));
+            const Neon::Backend& bk = pop[0].getBackend();
+            if (n > 0 && kind >= 0 && bk.getDeviceCount() == 1 && pop[0].getGrid().zHalo() == 0) {
+                nlbm_dense_desc d = pop[parity].getPartition(0).desc;
+                d.pop_in = pop[parity].getPartition(0).mem();
+                d.pop_out = pop[1 - parity].getPartition(0).mem();
+                d.flags = flag.getPartition(0).mem();
+                d.wall_cache = pop[1 - parity].wallCachePtr(0);
+                Neon::detail::check(nlbm_dense_step_n(kind, &d, pop[parity].wallCachePtr(0), mOmega, n, Neon::lbm::kernelOptions(),
+                                                      bk.stream(0, Neon::Backend::mainStreamIdx)),
+                                    "nlbm_dense_step_n");
+                parity = (parity + n) & 1;
+                return;
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            run();
+        }
+    }
+    /* whether runMany beats n x run() for this field (measured on B200): one dense partition of more than one
+     * chip-load of blocks (~400 000 cells) up to 2^24 cells */
+    auto chainPays() const -> bool
+    {
+        if constexpr (std::is_same_v<typename PopulationField::Grid, Neon::bGrid>) {
+            return false;
+        } else {
+            const auto   dim = pop[0].getDimension();
+            const size_t cells = dim.template rMul<size_t>();
+            return pop[0].getBackend().getDeviceCount() == 1 && pop[0].getGrid().zHalo() == 0 && cells > 400000 && cells <= (size_t(1) << 24);
+        }
+    }
     auto sync() -> void { pop[0].getBackend().syncAll(); }
     auto skeleton(int target) -> Neon::skeleton::Skeleton& { return lbmTwoPop[target]; }
 
    private:
     Neon::skeleton::Skeleton lbmTwoPop[2];
     PopulationField          pop[2];
+    CellTypeField            flag;
+    double                   mOmega = 0;
     int                      parity = 0;
 };
 

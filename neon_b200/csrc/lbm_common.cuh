@@ -144,6 +144,18 @@ struct MultiArgs
     int32_t     iterations;
     uint32_t    gx, gy, gz;  // the step kernel's launch grid: tiles to walk
     unsigned*   barrier;     // arrival counter of the grid-wide barrier (zero at launch)
+    int32_t     chainEarly;  // launch chain: planes that start on the plane counters (0: one chip-load of blocks, < 0: all)
+    int32_t     cooperative; // 1: one resident grid + grid-wide barrier (k_dense_multi); 0: a chain of dependent launches (k_dense_chain)
+};
+
+constexpr int kChainPlanesApi = 4096;  // planes a launch chain has counters for (lbm_step.cuh: kChainPlanes)
+// second argument of the chained step kernel (k_dense_chain, lbm_step.cuh): one launch per iteration, launched while its
+// predecessor still runs (programmatic dependent launch); a tile starts as soon as the planes it reads are complete
+struct ChainArgs
+{
+    unsigned* planeDone;  // one counter per z plane of the view: tiles that finished that plane, summed over the chain's iterations
+    unsigned  target;     // a tile of plane z starts once planeDone[z-1], [z], [z+1] >= target (0: first iteration, no wait)
+    unsigned  early;      // planes [0, early) start on the counters, the others behind griddepcontrol.wait; planes [0, early] publish
 };
 
 // ---------------------------------------------------------------- vector access

@@ -706,7 +706,7 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const void* __restr
     const int  specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
     const bool rowsInside = y >= 1 && y + 1 < a.ny && zm >= 1 && zm + 1 < a.nzm;  // every neighbouring row exists
     int        specAdj = -1, specSide = 0;
-    if (VEC > 1 && !COH && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {  // (cp.async goes through L1: not for COH)
+    if (VEC > 1 && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {  // (cp.async goes through L1: the multi-iteration kernel clears specXFix)
         if (x0 == 0)
             specAdj = 1;
         else if (x0 <= a.nx - 2 && a.nx - 2 < x0 + VEC) {
@@ -885,6 +885,59 @@ __global__ void __launch_bounds__(kStepThreads, 1) k_dense_multi(const DenseArgs
     }
 }
 
+// =============================================================== a chain of dependent launches (small boxes, the default of nlbm_dense_step_n)
+// One launch per iteration as in k_dense_step, but iteration t+1 is launched while iteration t still runs (programmatic
+// dependent launch: every block of t releases its dependents first thing, so t+1's blocks become resident as t's last blocks
+// leave), and the blocks of the first `early` planes — about one chip-load of blocks — do NOT wait for the whole predecessor
+// grid: a tile of plane z starts as soon as the tiles of planes z-1, z, z+1 of the previous iteration have finished — those wrote
+// every value it reads (RAW) and were the only readers of the cells it overwrites (WAR).  Launch gap and ramp-up of t+1 run in
+// the shadow of t's tail, which is most of what a small iteration costs as a kernel of its own.  Blocks of the later planes are
+// scheduled when the early ones leave; by then t is over and their griddepcontrol.wait returns at once, so only the early planes
+// pay for polling and only planes 0..early (what the early tiles of t+1 depend on) pay for publishing.
+// planeDone[z] counts finished tiles of plane z over the whole chain (a plane of iteration t+1 is only touched after the same
+// plane of t is complete, so the count is monotone in t).
+// Cannot deadlock: t+1 is launched only after EVERY block of t has started (that is what releases it), so whatever a block of
+// t+1 waits for — counters or the end of t — is resident or finished; by induction the same holds for t and t-1.  The grid of
+// the last iteration completes only after all earlier ones have, so the stream sees the chain as one piece of work.
+// Loads of the input field are ordinary coherent loads: behind griddepcontrol.wait, or behind one acquire fence per early block
+// (which also drops whatever the SM's L1 kept of the field two iterations ago; a line fetched after that fence belongs to a
+// complete plane and stays valid until the tiles of t+2 rewrite it, which wait for this block).
+template <class COL, typename T, int VEC>
+__global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_chain(const DenseArgs a, const ChainArgs c)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const bool first = threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0;
+    if (c.target != 0) {
+        if (blockIdx.z < c.early) {
+            if (first) {
+                const unsigned  z = blockIdx.z, zl = z > 0 ? z - 1 : 0, zh = z + 1 < gridDim.z ? z + 1 : z;
+                const unsigned *p0 = c.planeDone + zl, *p1 = c.planeDone + z, *p2 = c.planeDone + zh;
+                unsigned        v0, v1, v2;
+                for (;;) {
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(p0) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(p1) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(p2) : "memory");
+                    if (v0 >= c.target && v1 >= c.target && v2 >= c.target)
+                        break;
+                    __nanosleep(40);
+                }
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
+            __syncthreads();
+        } else {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
+    }
+    stepBody<COL, T, VEC, false, true>(a, a.in, a.out, a.keepCache, blockIdx.x, blockIdx.y, blockIdx.z);
+    if (blockIdx.z <= c.early) {  // what the early tiles of the next iteration wait for
+        __syncthreads();          // every store of the block is ordered before the arrival below (bar.sync + the fence's cumulativity)
+        if (first) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(c.planeDone + blockIdx.z) : "memory");
+        }
+    }
+}
+
 // Thread-block and grid shape of the direct kernel for one view (shared by the single-iteration and the multi-iteration launch)
 template <class COL, typename T, int VEC>
 inline void stepGeometry(DenseArgs& a, int nzView, int rowsLog2, int rpwSel, dim3& block, dim3& grid)
@@ -985,6 +1038,81 @@ inline unsigned* multiBarrierWord(int dev)
     return ring[dev] + (next[dev]++ & 63u);
 }
 
+// Plane counters of a launch chain: kChainPlanes words out of a small per-device ring (a chain owns its slice until 15 later
+// chains on the same device have been issued), allocated on first use and kept for the life of the process.
+constexpr int kChainPlanes = kChainPlanesApi;
+inline unsigned* chainPlaneCounters(int dev)
+{
+    static std::mutex mu;
+    static unsigned*  ring[64] = {};
+    static unsigned   next[64] = {};
+    if (dev < 0 || dev >= 64)
+        return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (ring[dev] == nullptr && cudaMalloc(reinterpret_cast<void**>(&ring[dev]), 16 * kChainPlanes * sizeof(unsigned)) != cudaSuccess)
+        return nullptr;
+    return ring[dev] + (size_t)(next[dev]++ & 15u) * kChainPlanes;
+}
+
+// `iterations` iterations as a chain of dependent launches (k_dense_chain); a.in / m.fieldB are the two fields
+template <class COL, typename T, int VEC>
+inline cudaError_t launchChainVec(DenseArgs a, const MultiArgs& m, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
+{
+    dim3 block, grid;
+    stepGeometry<COL, T, VEC>(a, nzView, rowsLog2, rpwSel, block, grid);
+    if (nzView <= 0 || m.iterations <= 0)
+        return cudaSuccess;
+    if (grid.y > 65535 || grid.z > (unsigned)kChainPlanes)
+        return cudaErrorInvalidConfiguration;
+    constexpr size_t keepBytes = stepKeepBytes<COL, T, VEC>();
+    int              dev = 0;
+    cudaError_t      e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && keepBytes > 48 * 1024)
+        e = cudaFuncSetAttribute(k_dense_chain<COL, T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)keepBytes);
+    if (e != cudaSuccess)
+        return e;
+    ChainArgs c;
+    c.planeDone = chainPlaneCounters(dev);
+    if (c.planeDone == nullptr)
+        return cudaErrorMemoryAllocation;
+    e = cudaMemsetAsync(c.planeDone, 0, grid.z * sizeof(unsigned), st);
+    if (e != cudaSuccess)
+        return e;
+    const void *fieldA = a.in, *fieldB = m.fieldB, *keepB = a.keepCache, *keepA = m.keepCacheA;
+    const unsigned tilesPerPlane = grid.x * grid.y;
+    // planes whose tiles start on the counters: one chip-load of blocks (what can be resident next to the predecessor's tail)
+    int sms = 0, perSm = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_dense_chain<COL, T, VEC>, kStepThreads, keepBytes);
+    if (e != cudaSuccess)
+        return e;
+    c.early = m.chainEarly != 0 ? (unsigned)m.chainEarly : ((unsigned)(sms * (perSm > 0 ? perSm : 1)) + tilesPerPlane - 1) / tilesPerPlane + 1;
+    if (c.early > grid.z)
+        c.early = grid.z;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = keepBytes;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    for (int it = 0; it < m.iterations; ++it) {
+        const bool even = (it & 1) == 0;
+        a.in = even ? fieldA : fieldB;
+        a.out = const_cast<void*>(even ? fieldB : fieldA);
+        a.keepCache = even ? keepB : keepA;
+        c.target = (unsigned)it * tilesPerPlane;
+        cfg.numAttrs = it > 0 ? 1 : 0;  // the first launch of a chain is an ordinary one: behind everything the stream holds
+        e = cudaLaunchKernelEx(&cfg, k_dense_chain<COL, T, VEC>, a, c);
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
+
 // `iterations` iterations in one cooperative launch (k_dense_multi); a.in / m.fieldB are the two fields
 template <class COL, typename T, int VEC>
 inline cudaError_t launchMultiVec(DenseArgs a, MultiArgs m, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
@@ -1069,6 +1197,15 @@ inline cudaError_t launchMulti(const DenseArgs& a, const MultiArgs& m, int nzVie
     }
     while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
         vec >>= 1;
+    if (!m.cooperative) {
+        if constexpr (maxVec >= 4) {
+            if (vec == 4)
+                return launchChainVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
+        }
+        if (vec >= 2)
+            return launchChainVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
+        return launchChainVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
+    }
     if constexpr (maxVec >= 4) {
         if (vec == 4)
             return launchMultiVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);

@@ -147,9 +147,11 @@ class LbmIteration:
               (27, "float32", "float32"): 3, (27, "float64", "float64"): 4}
 
     def runMany(self, iterations: int) -> None:
-        """``iterations`` iterations with ONE kernel launch (nlbm_dense_step_n: a resident grid that meets at a grid-wide barrier
-        between iterations) when the field lives on one device as a dense partition — the regime of small boxes, where an
-        iteration lasts ~10 us as a kernel of its own.  Anything else (several partitions, bGrid) runs ``iterations`` x run()."""
+        """``iterations`` iterations with ONE library call (nlbm_dense_step_n) when the field lives on one device as a dense
+        partition — the regime of small boxes, where an iteration lasts ~10 us as a kernel of its own.  By default a chain of
+        dependent launches whose tiles wait plane-wise for the previous iteration (launch gap, ramp-up and tail of consecutive
+        iterations overlap); with ``opts = opt_kernel(KERNEL_COOPERATIVE)`` one resident grid and a grid-wide barrier.
+        Anything else (several partitions, bGrid) runs ``iterations`` x run()."""
         f = self.pop[self.parity]
         g = f.grid
         bk = g.backend
@@ -165,9 +167,22 @@ class LbmIteration:
         capi.call("nlbm_dense_step_n", kind, C.byref(desc), fin.wallCachePtr(), self.omega, iterations, o, bk.streamHandle(0))
         self.parity ^= iterations & 1
 
-    def runGraph(self, iterations: int) -> int:
+    def chainPays(self) -> bool:
+        """Whether runMany's launch chain beats a replay of single-iteration launches for this field: one dense partition of
+        more than ~400 000 cells (below, an iteration is one chip-load of blocks and the chain is bound by the latency of one
+        tile like the kernel itself: 64^3 22.2 against 24.1 GLUPS) up to 2^24 cells (256^3: +1.7 %; no difference above).
+        Measured on B200, profiles/r02o_small_sweep.log: 80^3 +3.6 %, 96^3 +6 %, 128^3 +7.8 %, 160^3 +4 %, 192^3 +3.4 %."""
+        g = self.pop[0].grid
+        bk = g.backend
+        if bk.world > 1 or bk.runtime != Runtime.stream or self.fused is not None or getattr(g, "kind", "dense") != "dense" or g.z_halo != 0:
+            return False
+        cells = g.dim[0] * g.dim[1] * g.dim[2]
+        return 400_000 < cells <= (1 << 24)
+
+    def runGraph(self, iterations: int, many: Optional[bool] = None) -> int:
         """ONE device: ``iterations`` (rounded up to an even count, so that the field parity is back where it started)
-        captured once into a CUDA graph and replayed with one host call.  For boxes of a few hundred thousand cells one
+        captured once into a CUDA graph and replayed with one host call (``many``: one runMany(n) call — the launch chain —
+        instead of n run() calls; default: whichever is faster for the box, chainPays()).  For boxes of a few hundred thousand cells one
         iteration takes ~10 us on a B200 — the host cannot issue launches that fast, and a launch costs as much as the
         kernel.  (The reference re-parses the loading lambda and calls cudaFuncGetAttributes for every launch,
         libNeonSys/include/Neon/sys/devices/gpu/GpuDevice.h:151-191.)  Returns the number of iterations actually run."""
@@ -178,19 +193,28 @@ class LbmIteration:
             for _ in range(n):
                 self.run()
             return n
+        if many is None:
+            many = self.chainPays()
         cache = self.__dict__.setdefault("_graphs", {})
-        key = (n, self.parity)
+        key = (n, self.parity, many)
         main = bk.stream(0)
         if key not in cache:
-            self.run()  # make sure every lazily built object (x-face caches, attributes) exists before the capture
-            self.run()
+            # make sure every lazily built object (x-face caches, function attributes, the chain's counters) exists before the capture
+            if many:
+                self.runMany(2)
+            else:
+                self.run()
+                self.run()
             main.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.stream(main):
                 g.capture_begin()
                 try:
-                    for _ in range(n):
-                        self.run()
+                    if many:  # the launch chain of runMany (memset of its plane counters + n dependent launches) as one graph
+                        self.runMany(n)
+                    else:
+                        for _ in range(n):
+                            self.run()
                 finally:
                     g.capture_end()
             cache[key] = g

@@ -152,6 +152,23 @@ def test_ragged_partitions_and_device_setup(app, tmp_path, golden_dir):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dim,warm", [((100, 80, 60), 0), ((128, 64, 64), 7)])
+def test_small_box_launch_chain_matches_the_oracle(app, tmp_path, oracle, dim, warm):
+    """One dense partition of more than ~400 000 cells in benchmark mode: the app runs up to 10 iterations per library call
+    (LbmIterationT::runMany -> nlbm_dense_step_n, the chain of dependent launches) — the oracle's bits, with a chunk that ends at
+    the warm-up boundary and an odd remainder."""
+    O = oracle
+    iters = 23
+    cls = O.classify(O.GEOM_CAVITY_SPHERE, *dim)
+    mask = O.wall_mask(19, cls)
+    ref = O.run(19, O.init_pop(19, cls, np.float32), cls, mask, O.omega_cavity(dim[0]), iters)  # (the app's N is dim.x)
+    d = _dump(app, str(tmp_path), dim, "float", "sphere", iters, extra=("--warmup-iter", warm))
+    assert d["omega"] == O.omega_cavity(dim[0])
+    assert np.array_equal(d["mask"], mask)
+    assert np.array_equal(d["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fp,parts", [("double", 1), ("double", 3), ("float", 2)])
 def test_d3q27_against_the_oracle(app, tmp_path, oracle, fp, parts):
     O = oracle

@@ -206,10 +206,12 @@ def test_reference_bits_outside_the_guard_of_the_lean_evaluation(nb, bk, oracle,
                                                     (19, np.float64, (33, 17, 12), 2, 6), (27, np.float32, (70, 20, 24), 1, 4),
                                                     (19, np.float32, (300, 40, 30), 1, 3)])
 def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, iters):
-    """nlbm_dense_step_n (LbmIteration.runMany): a resident grid iterates with a grid-wide barrier between iterations, reading
-    the field the previous iteration wrote through L2.  Same bits as the oracle in REFERENCE arithmetic, the same bits as
-    iteration-by-iteration launches in FAST arithmetic, odd and even iteration counts (where the result lands), more tiles than
-    resident blocks (300 x 40 x 30) and fewer."""
+    """nlbm_dense_step_n (LbmIteration.runMany).  Default: a chain of dependent launches, iteration t+1 launched while t still
+    runs, every tile waiting plane-wise for the tiles of the previous iteration it depends on; KERNEL_COOPERATIVE: a resident grid
+    with a grid-wide barrier between iterations.  Both read the field the previous iteration wrote through coherent loads.  Same
+    bits as the oracle in REFERENCE arithmetic, the same bits as iteration-by-iteration launches in FAST arithmetic, odd and even
+    iteration counts (where the result lands), more tiles than resident blocks (300 x 40 x 30) and fewer, every vector width, and
+    the chain captured into a CUDA graph and replayed."""
     from neon_b200 import problems as P
     nx, ny, nz = dim
     cls = oracle.classify(geom, nx, ny, nz)
@@ -217,20 +219,34 @@ def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, i
     pop = oracle.init_pop(q, cls, store)
     omega = oracle.omega_cavity(max(dim))
     ref = oracle.run(q, pop, cls, mask, omega, iters + 1)
+    one = None
     for arith in (nb.ARITH_REFERENCE, nb.ARITH_FAST):
-        grid = nb.dGrid(bk, dim)
-        pop0, pop1, flag = P.setup_host(grid, q, store, cls, pop)
-        it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q, arith=arith)
-        it.runMany(iters)       # one launch
-        it.runMany(1)           # and one more through the same entry point: parity bookkeeping
-        bk.syncAll()
-        many = it.getInput().updateHostData()
-        if arith == nb.ARITH_REFERENCE:
-            assert np.array_equal(many.view(np.uint8), ref.view(np.uint8))
-        else:
-            one, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters + 1, nb.ARITH_FAST)
-            assert np.array_equal(many.view(np.uint8), one.view(np.uint8))
-        assert np.array_equal(flag.masks(), mask)
+        for mode in (0, nb.opt_kernel(nb.KERNEL_COOPERATIVE), nb.opt_vec(1), nb.opt_vec(2), nb.opt_vec(4), 15 << 16, 2 << 16):  # (NLBM_OPT_CHAIN_EARLY: all planes / two planes on the counters)
+            grid = nb.dGrid(bk, dim)
+            pop0, pop1, flag = P.setup_host(grid, q, store, cls, pop)
+            it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q, arith=arith,
+                                 opts=mode)
+            it.runMany(iters)       # one library call
+            it.runMany(1)           # and one more through the same entry point: parity bookkeeping
+            bk.syncAll()
+            many = it.getInput().updateHostData()
+            if arith == nb.ARITH_REFERENCE:
+                assert np.array_equal(many.view(np.uint8), ref.view(np.uint8)), f"mode {mode:#x}"
+            else:
+                if one is None:
+                    one, _ = run_cuda(nb, bk, q, store, cls, pop, omega, iters + 1, nb.ARITH_FAST)
+                assert np.array_equal(many.view(np.uint8), one.view(np.uint8)), f"mode {mode:#x}"
+            assert np.array_equal(flag.masks(), mask)
+    # the chain inside a CUDA graph, replayed: 2 plain + 3 x n iterations
+    n = iters + (iters & 1)
+    grid = nb.dGrid(bk, dim)
+    pop0, pop1, flag = P.setup_host(grid, q, store, cls, pop)
+    it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q, arith=nb.ARITH_REFERENCE)
+    done = it.runGraph(n, many=True) + it.runGraph(n, many=True) + it.runGraph(n, many=True)
+    bk.syncAll()
+    assert done == 3 * n + 2
+    ref3 = oracle.run(q, pop, cls, mask, omega, done)
+    assert np.array_equal(it.getInput().updateHostData().view(np.uint8), ref3.view(np.uint8))
 
 
 def test_device_setup_matches_oracle(nb, bk, oracle):

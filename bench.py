@@ -52,8 +52,7 @@ def parse():
     ap.add_argument("--arith", default="fast", choices=["fast", "reference"])
     ap.add_argument("--occ", default="standard", choices=["none", "standard"])
     ap.add_argument("--transport", default="auto", choices=["auto", "packed", "views", "ipc", "fused"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "tma", "coop"],
-                    help="coop: with --persistent, the resident grid + grid-wide barrier instead of the launch chain")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "tma"])
     ap.add_argument("--vec", type=int, default=0)
     ap.add_argument("--tma-l2promo", type=int, default=0)
     ap.add_argument("--tma-groups", type=int, default=0)
@@ -70,7 +69,7 @@ def parse():
     ap.add_argument("--graph-iters", type=int, default=-1,
                     help="one device: iterations per host call — a CUDA-graph replay, or one multi-iteration launch with --persistent "
                          "(0 = plain launches; default: 0 for boxes above 2^22 cells, else 10)")
-    ap.add_argument("--persistent", action="store_true", help="nlbm_dense_step_n called directly (G iterations per call, no CUDA graph); with --kernel coop its resident-grid variant")
+    ap.add_argument("--persistent", action="store_true", help="nlbm_dense_step_n called directly (G iterations per call, no CUDA graph)")
     ap.add_argument("--chain-early", type=int, default=0, help="with --persistent: NLBM_OPT_CHAIN_EARLY (0 default, 1..14: 2^(e-1) planes start on the plane counters, 15: all)")
     ap.add_argument("--chain-graph", action="store_true", help="graph replay of the launch chain whatever the box size")
     ap.add_argument("--no-chain", action="store_true", help="graph replay of single-iteration launches whatever the box size")
@@ -299,7 +298,7 @@ class Job:
     def opts(self):
         a, nb = self.args, self.nb
         from neon_b200._capi import opt_tma
-        return nb.opt_vec(a.vec) | nb.opt_rows_log2(a.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2, "coop": 3}[a.kernel]) \
+        return nb.opt_vec(a.vec) | nb.opt_rows_log2(a.rows_log2) | nb.opt_kernel({"auto": 0, "direct": 1, "tma": 2}[a.kernel]) \
             | opt_tma(a.tma_l2promo, a.tma_groups) | ((1 << 20) if a.flags_summary_first else 0) | ((a.rpw & 7) << 21) \
             | ((a.experiment & 7) << 24) | ((1 << 27) if a.no_xface_prefetch else 0) | a.opts_extra | ((a.chain_early & 15) << 16)
 
@@ -349,7 +348,7 @@ class Job:
         small_mode = "plain launches"
         if graph_iters > 1 and not is_block and args.persistent:
             per_call = graph_iters + (graph_iters & 1)  # LbmIteration.runMany: G iterations per library call, not captured
-            small_mode = "nlbm_dense_step_n (resident grid, grid-wide barrier)" if args.kernel == "coop" else "nlbm_dense_step_n launch chain, direct calls"
+            small_mode = "nlbm_dense_step_n launch chain, direct calls"
 
             def runner():
                 it.runMany(per_call)
@@ -387,7 +386,7 @@ class Job:
         nnb = (dn is not None) + (up is not None)
         pipelined = self.world > 1 and not args.no_pipeline and args.transport in ("auto", "ipc") and occ != nb.Occ.none
         if self.world == 1:
-            launches_step = 1.0 / per_call if (graph_iters > 1 and not is_block and args.persistent and args.kernel == "coop") else 1
+            launches_step = 1
         elif args.transport == "fused":
             launches_step = 1 + nnb  # step+push kernel, one flag wait per neighbour
         elif pipelined:
@@ -415,7 +414,7 @@ class Job:
         key = f"d3q{q}_{'f32' if dtype.itemsize == 4 else 'f64'}_{dim[0]}x{dim[1]}x{cells_rank // (dim[0] * dim[1])}" + ("_bgrid" if is_block else "")
         traffic = self.traffic.get(key, {}).get("dram_bytes_per_launch") if arith_name == "fast" else None
         l2_note = "inputs exceed L2 (two population fields of %.2f GB per GPU)" % (q * cells_rank * dtype.itemsize / 1e9)
-        roofline = {"bound": "hbm", "kernel": "k_block_step" if is_block else ("k_dense_chain" if "chain" in small_mode else ("k_dense_multi" if "resident" in small_mode else "k_dense_step")), "achieved": achieved, "peak": self.peak,
+        roofline = {"bound": "hbm", "kernel": "k_block_step" if is_block else ("k_dense_chain" if "chain" in small_mode else "k_dense_step"), "achieved": achieved, "peak": self.peak,
                     "unit": "GB/s", "frac": achieved / self.peak, "traffic": traffic, "bytes_per_cell": bytes_cell,
                     "cells_per_launch": cells_rank, "kernel_ms": kern_ms, "peak_source": self.peak_src,
                     "frac_of_nominal_8TBps": achieved / 8000.0}
@@ -429,7 +428,7 @@ class Job:
                "dtype": "f32" if dtype.itemsize == 4 else "f64", "arith": arith_name, "dim": list(dim), "lattice": f"D3Q{q}",
                "grid": "bGrid" if is_block else "dGrid", "roofline": roofline, "gpu_launches": int(round(launches_step * steps)),
                "graph_iters": per_call if graph_iters > 1 else 0,
-               "iterations_per_launch": per_call if (graph_iters > 1 and not is_block and args.persistent and args.kernel == "coop") else 1,
+               "iterations_per_launch": 1,
                "issue": small_mode, "l2": l2_note, "clocks": clocks,
                "partition": ((f"{grid.n_blocks} blocks per GPU" if is_block else f"z-slabs of {grid.nz_local} planes")
                              if self.world > 1 else "single partition")}

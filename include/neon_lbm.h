@@ -117,7 +117,6 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 #define NLBM_KERNEL_AUTO 0
 #define NLBM_KERNEL_DIRECT 1
 #define NLBM_KERNEL_TMA 2
-#define NLBM_KERNEL_COOPERATIVE 3 /* nlbm_dense_step_n only: one resident grid + grid-wide barrier instead of the launch chain */
 
 /* Dense (dGrid) partition descriptor: one z-slab of the global box on one GPU.
  * Replaces what the reference kernel receives by value: dSpan {dataView, zHalo,
@@ -240,9 +239,11 @@ typedef struct nlbm_peer_desc {
  * as much as the work.  Default: a CHAIN of dependent launches (programmatic dependent launch, one per iteration): iteration t+1
  * is launched while t still runs, and a tile of plane z starts as soon as planes z-1, z, z+1 of the previous iteration are
  * complete (per-plane counters in device memory) — no grid ever waits for a whole grid, so launch gap, ramp-up and tail of
- * consecutive iterations overlap.  NLBM_OPT_KERNEL(NLBM_KERNEL_COOPERATIVE): one resident grid (cooperative launch) that walks
- * the tiles and meets at a grid-wide barrier between iterations (measured slower; also used when the view has more than 4096
- * planes).  Same results as `iterations` step calls, bit for bit.  Capturable into a CUDA graph.                              */
+ * consecutive iterations overlap.  Only the first chip-load of planes of an iteration polls (NLBM_OPT_CHAIN_EARLY); the blocks
+ * behind them are scheduled when the previous launch is over and pass griddepcontrol.wait at once.  A view of more than 4096
+ * planes runs as `iterations` ordinary step launches.  (A single resident grid with a grid-wide barrier between iterations was
+ * built and measured in round 2 — 16.5 us per 64^3 iteration against 11.8: profiles/r02k_multi64_*, r02l_* — and retired.)
+ * Same results as `iterations` step calls, bit for bit.  Capturable into a CUDA graph.                                        */
 int nlbm_dense_step_n(int kind, const nlbm_dense_desc* d, const void* wall_cache_in, double omega, int iterations, int opts, void* stream);
 
 int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream);

@@ -28,7 +28,7 @@ def opt_rows_log2(r: int) -> int:
     return (r & 0xF) << 8
 
 
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_COOPERATIVE = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 
 
 def opt_kernel(k: int) -> int:

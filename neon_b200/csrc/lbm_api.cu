@@ -241,7 +241,7 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
         } else if (kernelSel == 2) {
             return fail(NLBM_ERR_CUDA, "cannot build the TMA descriptor (cuTensorMapEncodeTiled unavailable or refused)");
         }
-    } else if (kernelSel != 0 && kernelSel != 1 && !(kernelSel == NLBM_KERNEL_COOPERATIVE && iterations > 0)) {
+    } else if (kernelSel != 0 && kernelSel != 1) {
         return fail(NLBM_ERR_INVALID, "bad kernel selector %d", kernelSel);
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -252,11 +252,8 @@ int stepImpl(nlbm::StepKind kind, int elemBytes, const nlbm_dense_desc* d, doubl
         m.fieldB = d->pop_out;
         m.keepCacheA = wallCacheIn;
         m.iterations = iterations;
-        // default: a chain of dependent launches with plane-wise dependencies; NLBM_KERNEL_COOPERATIVE: one resident grid and a
-        // grid-wide barrier (measured slower).  More planes than the chain has counters: the resident grid
         const int ce = (opts >> 16) & 0xF;  // NLBM_OPT_CHAIN_EARLY
         m.chainEarly = ce == 0 ? 0 : (ce == 15 ? -1 : 1 << (ce - 1));
-        m.cooperative = (kernelSel == NLBM_KERNEL_COOPERATIVE || nzView > nlbm::kChainPlanesApi) ? 1 : 0;
         cudaError_t e = arith == NLBM_ARITH_REFERENCE ? nlbm::launchMultiRef(kind, a, m, l, st) : nlbm::launchMultiFast(kind, a, m, l, st);
         if (e != cudaSuccess)
             return cudaFail(e, "dense multi-iteration launch");

@@ -136,16 +136,13 @@ struct DenseArgs
     uint32_t  signalValue, warpsPerFace;
 };
 
-// second argument of the multi-iteration kernel (k_dense_multi, lbm_step.cuh)
+// nlbm_dense_step_n: the second field of the two-field scheme and how the chain of launches is issued (lbm_step.cuh)
 struct MultiArgs
 {
     const void* fieldB;      // the second field: iteration t reads (t even ? a.in : fieldB) and writes the other one
     const void* keepCacheA;  // x-face cache of a.in (a.keepCache is a.out's, i.e. fieldB's); may be null like a.keepCache
     int32_t     iterations;
-    uint32_t    gx, gy, gz;  // the step kernel's launch grid: tiles to walk
-    unsigned*   barrier;     // arrival counter of the grid-wide barrier (zero at launch)
-    int32_t     chainEarly;  // launch chain: planes that start on the plane counters (0: one chip-load of blocks, < 0: all)
-    int32_t     cooperative; // 1: one resident grid + grid-wide barrier (k_dense_multi); 0: a chain of dependent launches (k_dense_chain)
+    int32_t     chainEarly;  // planes that start on the plane counters (0: one chip-load of blocks, < 0: all)
 };
 
 constexpr int kChainPlanesApi = 4096;  // planes a launch chain has counters for (lbm_step.cuh: kChainPlanes)

@@ -26,7 +26,7 @@ struct StepLaunch
 };
 cudaError_t launchStepRef(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
 cudaError_t launchStepFast(StepKind kind, const DenseArgs& a, const StepLaunch& l, cudaStream_t st);
-// several iterations in one cooperative launch (direct kernel only); m names the second field
+// nlbm_dense_step_n: several iterations as a chain of dependent launches (direct kernel only); m names the second field
 struct MultiArgs;
 cudaError_t launchMultiRef(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st);
 cudaError_t launchMultiFast(StepKind kind, const DenseArgs& a, const MultiArgs& m, const StepLaunch& l, cudaStream_t st);

@@ -706,7 +706,7 @@ __device__ __forceinline__ void stepBody(const DenseArgs& a, const void* __restr
     const int  specCell = (VEC > 1 && a.prefetchXFaces && rowOk && a.nx > VEC) ? (x0 == 0 ? 0 : (x0 + VEC >= a.nx && x0 < a.nx ? a.nx - 1 - x0 : -1)) : -1;
     const bool rowsInside = y >= 1 && y + 1 < a.ny && zm >= 1 && zm + 1 < a.nzm;  // every neighbouring row exists
     int        specAdj = -1, specSide = 0;
-    if (VEC > 1 && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {  // (cp.async goes through L1: the multi-iteration kernel clears specXFix)
+    if (VEC > 1 && a.specXFix && rowOk && rowsInside && a.nx > 2 * VEC) {  // 
         if (x0 == 0)
             specAdj = 1;
         else if (x0 <= a.nx - 2 && a.nx - 2 < x0 + VEC) {
@@ -832,57 +832,6 @@ template <class COL, typename T, int VEC, bool PEER>
 __global__ void __launch_bounds__(kStepThreads, stepMinBlocks(COL::Q * VEC * (int)sizeof(T) / 4)) k_dense_step(const DenseArgs a)
 {
     stepBody<COL, T, VEC, PEER, false>(a, a.in, a.out, a.keepCache, blockIdx.x, blockIdx.y, blockIdx.z);
-}
-
-// =============================================================== several iterations in ONE launch
-// For boxes of a few hundred thousand cells one iteration lasts ~10 us as a kernel of its own: the launch, the ramp-up of a
-// grid that fills the chip once and the tail cost as much as the work.  k_dense_multi keeps one resident grid (cooperative
-// launch, as many blocks as fit) alive over `iterations` iterations: every block walks the tiles of the step kernel's launch
-// grid with a stride, all blocks meet at a grid-wide barrier, the two fields swap roles, and so on.  While both fields fit the
-// 126 MB L2 (up to ~96^3 D3Q19 fp32) the populations never leave the chip.  Same tile code as k_dense_step (stepBody), with the
-// input field read through L2.  STANDARD view of a partition without neighbours (nothing is exchanged between iterations).
-
-// Grid-wide barrier of the multi-iteration kernel.  cooperative_groups' grid.sync() spins on an ACQUIRE load, which on sm_100a
-// invalidates the SM's L1 on every spin (ncu r02k: CCTL.IVALL executed 800 000 times in ten iterations of a 64^3 box) — also for
-// the co-resident block that is still computing.  Here one thread per block announces its arrival (release), spins on a RELAXED
-// load with a back-off, and the block passes ONE acquire fence afterwards.  `counter` counts arrivals since the launch: the
-// barrier after iteration t is open once it reaches (t + 1) * gridDim.x.
-__device__ __forceinline__ void gridBarrier(unsigned* counter, const unsigned target)
-{
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
-        unsigned seen;
-        asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
-        ++seen;
-        while (seen < target) {
-            __nanosleep(64);
-            asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-        }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    }
-    __syncthreads();
-}
-
-// One block per SM and no register cap: the tile loop keeps a dozen values alive across the tile code, and at the 128
-// registers of the step kernel they spill — which costs an L2 round trip each here, because every barrier invalidates L1.
-template <class COL, typename T, int VEC>
-__global__ void __launch_bounds__(kStepThreads, 1) k_dense_multi(const DenseArgs a, const MultiArgs m)
-{
-    const unsigned tiles = m.gx * m.gy * m.gz;
-    for (int it = 0; it < m.iterations; ++it) {
-        // the kernel arguments stay where they are (constant bank); only the three pointers that swap are selected here
-        const bool  even = (it & 1) == 0;
-        const void* fin = even ? a.in : m.fieldB;
-        void*       fout = const_cast<void*>(even ? m.fieldB : a.in);
-        const void* keep = even ? a.keepCache : m.keepCacheA;
-        for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const unsigned bx = t % m.gx, by = (t / m.gx) % m.gy, bz = t / (m.gx * m.gy);
-            stepBody<COL, T, VEC, false, true>(a, fin, fout, keep, bx, by, bz);
-        }
-        // every store of this iteration is visible before anybody reads the field in the next one
-        if (it + 1 < m.iterations)
-            gridBarrier(m.barrier, (unsigned)(it + 1) * gridDim.x);
-    }
 }
 
 // =============================================================== a chain of dependent launches (small boxes, the default of nlbm_dense_step_n)
@@ -1023,21 +972,6 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     return cudaGetLastError();
 }
 
-// Arrival counters of the multi-iteration kernel's barrier: 64 words per device, handed out round-robin (a launch owns its word
-// until 63 later launches on the same device have been issued), allocated on first use and kept for the life of the process.
-inline unsigned* multiBarrierWord(int dev)
-{
-    static std::mutex mu;
-    static unsigned*  ring[64] = {};
-    static unsigned   next[64] = {};
-    if (dev < 0 || dev >= 64)
-        return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (ring[dev] == nullptr && cudaMalloc(reinterpret_cast<void**>(&ring[dev]), 64 * sizeof(unsigned)) != cudaSuccess)
-        return nullptr;
-    return ring[dev] + (next[dev]++ & 63u);
-}
-
 // Plane counters of a launch chain: kChainPlanes words out of a small per-device ring (a chain owns its slice until 15 later
 // chains on the same device have been issued), allocated on first use and kept for the life of the process.
 constexpr int kChainPlanes = kChainPlanesApi;
@@ -1113,47 +1047,6 @@ inline cudaError_t launchChainVec(DenseArgs a, const MultiArgs& m, int nzView, i
     return cudaSuccess;
 }
 
-// `iterations` iterations in one cooperative launch (k_dense_multi); a.in / m.fieldB are the two fields
-template <class COL, typename T, int VEC>
-inline cudaError_t launchMultiVec(DenseArgs a, MultiArgs m, int nzView, int rowsLog2, int rpwSel, cudaStream_t st)
-{
-    dim3 block, grid;
-    stepGeometry<COL, T, VEC>(a, nzView, rowsLog2, rpwSel, block, grid);
-    if (nzView <= 0 || m.iterations <= 0)
-        return cudaSuccess;
-    a.specXFix = 0;  // those operands change every iteration and cp.async fetches through L1
-    m.gx = grid.x;
-    m.gy = grid.y;
-    m.gz = grid.z;
-    constexpr size_t keepBytes = stepKeepBytes<COL, T, VEC>();
-    int              dev = 0, sms = 0, perSm = 0;
-    cudaError_t      e = cudaGetDevice(&dev);
-    if (e == cudaSuccess)
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess && keepBytes > 48 * 1024)
-        e = cudaFuncSetAttribute(k_dense_multi<COL, T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)keepBytes);
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_dense_multi<COL, T, VEC>, kStepThreads, keepBytes);
-    if (e != cudaSuccess)
-        return e;
-    if (perSm < 1)
-        return cudaErrorLaunchOutOfResources;
-    const unsigned long long tiles = (unsigned long long)grid.x * grid.y * grid.z;
-    unsigned                 blocks = (unsigned)sms * (unsigned)perSm;
-    if (blocks > tiles)
-        blocks = (unsigned)tiles;
-    // arrival counter of the grid-wide barrier: one word of a small per-device ring, zeroed in stream order before the launch
-    m.barrier = multiBarrierWord(dev);
-    if (m.barrier == nullptr)
-        return cudaErrorMemoryAllocation;
-    e = cudaMemsetAsync(m.barrier, 0, sizeof(unsigned), st);
-    if (e != cudaSuccess)
-        return e;
-    void* args[] = {&a, &m};
-    // cooperative launch: the runtime guarantees that all blocks are resident, which the barrier needs
-    return cudaLaunchCooperativeKernel((const void*)k_dense_multi<COL, T, VEC>, dim3(blocks), block, args, keepBytes, st);
-}
-
 template <class COL, typename T>
 inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
 {
@@ -1186,9 +1079,24 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
     return launchStepVec<COL, T, 1>(a, nzView, rowsLog2, rpwSel, st);
 }
 
+// nlbm_dense_step_n: the launch chain; a view with more planes than the chain has counters runs as plain step launches
 template <class COL, typename T>
 inline cudaError_t launchMulti(const DenseArgs& a, const MultiArgs& m, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
 {
+    if (nzView > kChainPlanes) {
+        DenseArgs   b = a;
+        const void *fieldA = a.in, *keepB = a.keepCache;
+        for (int it = 0; it < m.iterations; ++it) {
+            const bool even = (it & 1) == 0;
+            b.in = even ? fieldA : m.fieldB;
+            b.out = const_cast<void*>(even ? m.fieldB : fieldA);
+            b.keepCache = even ? keepB : m.keepCacheA;
+            cudaError_t e = launchStep<COL, T>(b, nzView, vec, rowsLog2, rpwSel, st);
+            if (e != cudaSuccess)
+                return e;
+        }
+        return cudaSuccess;
+    }
     constexpr int maxVec = 16 / (int)sizeof(T);
     if (vec <= 0 || vec > maxVec) {
         vec = maxVec;
@@ -1197,22 +1105,13 @@ inline cudaError_t launchMulti(const DenseArgs& a, const MultiArgs& m, int nzVie
     }
     while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
         vec >>= 1;
-    if (!m.cooperative) {
-        if constexpr (maxVec >= 4) {
-            if (vec == 4)
-                return launchChainVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
-        }
-        if (vec >= 2)
-            return launchChainVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
-        return launchChainVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
-    }
     if constexpr (maxVec >= 4) {
         if (vec == 4)
-            return launchMultiVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
+            return launchChainVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
     }
     if (vec >= 2)
-        return launchMultiVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
-    return launchMultiVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
+        return launchChainVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
+    return launchChainVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
 }
 
 }  // namespace nlbm

@@ -148,9 +148,9 @@ class LbmIteration:
 
     def runMany(self, iterations: int) -> None:
         """``iterations`` iterations with ONE library call (nlbm_dense_step_n) when the field lives on one device as a dense
-        partition — the regime of small boxes, where an iteration lasts ~10 us as a kernel of its own.  By default a chain of
-        dependent launches whose tiles wait plane-wise for the previous iteration (launch gap, ramp-up and tail of consecutive
-        iterations overlap); with ``opts = opt_kernel(KERNEL_COOPERATIVE)`` one resident grid and a grid-wide barrier.
+        partition — the regime of small boxes, where an iteration lasts ~10 us as a kernel of its own: a chain of dependent
+        launches whose first tiles wait plane-wise for the previous iteration (launch gap, ramp-up and tail of consecutive
+        iterations overlap).
         Anything else (several partitions, bGrid) runs ``iterations`` x run()."""
         f = self.pop[self.parity]
         g = f.grid

@@ -30,11 +30,11 @@ def main():
         if not opts:
             it.runMany(3)  # several iterations in one library call: the chain of dependent launches (plane-wise waits, coherent loads)
             it.runMany(2)
-            coop = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, 1.3, lattice_q=q, arith=arith,
-                                   opts=nb.opt_kernel(nb.KERNEL_COOPERATIVE))
-            coop.parity = it.parity
-            coop.runMany(3)  # ... and the resident grid with its grid-wide barrier
-            it.parity = coop.parity
+            every = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, 1.3, lattice_q=q, arith=arith,
+                                    opts=15 << 16)  # NLBM_OPT_CHAIN_EARLY(15): every plane on the counters
+            every.parity = it.parity
+            every.runMany(3)
+            it.parity = every.parity
         bk.syncAll()
         assert np.isfinite(it.getInput().updateHostData()).all()
     # REFERENCE arithmetic on a lid far outside the guard of its lean evaluation: fast and plain path inside the same warps

@@ -206,9 +206,9 @@ def test_reference_bits_outside_the_guard_of_the_lean_evaluation(nb, bk, oracle,
                                                     (19, np.float64, (33, 17, 12), 2, 6), (27, np.float32, (70, 20, 24), 1, 4),
                                                     (19, np.float32, (300, 40, 30), 1, 3)])
 def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, iters):
-    """nlbm_dense_step_n (LbmIteration.runMany).  Default: a chain of dependent launches, iteration t+1 launched while t still
-    runs, every tile waiting plane-wise for the tiles of the previous iteration it depends on; KERNEL_COOPERATIVE: a resident grid
-    with a grid-wide barrier between iterations.  Both read the field the previous iteration wrote through coherent loads.  Same
+    """nlbm_dense_step_n (LbmIteration.runMany): a chain of dependent launches, iteration t+1 launched while t still runs, the
+    tiles of the first planes waiting plane-wise for the tiles of the previous iteration they depend on, the others for the end of
+    the previous launch; the field the previous iteration wrote is read through coherent loads.  Same
     bits as the oracle in REFERENCE arithmetic, the same bits as iteration-by-iteration launches in FAST arithmetic, odd and even
     iteration counts (where the result lands), more tiles than resident blocks (300 x 40 x 30) and fewer, every vector width, and
     the chain captured into a CUDA graph and replayed."""
@@ -221,7 +221,7 @@ def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, i
     ref = oracle.run(q, pop, cls, mask, omega, iters + 1)
     one = None
     for arith in (nb.ARITH_REFERENCE, nb.ARITH_FAST):
-        for mode in (0, nb.opt_kernel(nb.KERNEL_COOPERATIVE), nb.opt_vec(1), nb.opt_vec(2), nb.opt_vec(4), 15 << 16, 2 << 16):  # (NLBM_OPT_CHAIN_EARLY: all planes / two planes on the counters)
+        for mode in (0, nb.opt_vec(1), nb.opt_vec(2), nb.opt_vec(4), 15 << 16, 2 << 16):  # (NLBM_OPT_CHAIN_EARLY: all planes / two planes on the counters)
             grid = nb.dGrid(bk, dim)
             pop0, pop1, flag = P.setup_host(grid, q, store, cls, pop)
             it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q, arith=arith,

@@ -338,6 +338,9 @@ class Job:
         graph_iters = args.graph_iters
         if graph_iters < 0:
             graph_iters = 10 if (self.world == 1 and cells <= (1 << 24)) else 0
+            # the launch chain starts every replay with an ordinary launch (behind a memset of its counters): longer replays, fewer drains
+            if graph_iters and not is_block and 400_000 < cells and not args.no_chain and steps >= 100:
+                graph_iters = 50
         if self.world > 1:
             graph_iters = 0
         it = nb.LbmIteration(nb.StencilSemantic.streaming, occ, nb.TransferMode.get, pop0, pop1, flag, omega, lattice_q=q,

@@ -61,6 +61,10 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 #define NLBM_FLAG_MASK_BITS 0x07FFFFFFu
 #define NLBM_FLAG_CLASS_SHIFT 28
 #define NLBM_FLAG_CLASS(f) (((f) >> NLBM_FLAG_CLASS_SHIFT) & 3u)
+/* bGrid only, bit 30 of the flag word of a block's FIRST cell: every cell of the block is bulk without a wall neighbour.  Set by
+ * nlbm_block_wall_mask, cleared by whoever rewrites the word; the block step kernels then skip the block's flag words.  Not part
+ * of the cell's flags: decode with NLBM_FLAG_CLASS / NLBM_FLAG_MASK_BITS.                                                  */
+#define NLBM_FLAG_BLOCK_PLAIN 0x40000000u
 
 /* Arithmetic mode (bits 0..3 of `opts`).
  * REFERENCE reproduces the rounding of the reference expressions bit for bit
@@ -109,7 +113,9 @@ typedef enum nlbm_cell_class { NLBM_BOUNCE_BACK = 0, NLBM_MOVING_WALL = 1, NLBM_
 /* bit 28 (direct kernel): fetch the 4-byte flag word of EVERY cell together with the populations (the round-1 default).
  * Default (bit clear): each thread reads one byte of the cell map (1 byte per 4 cells, kept behind the flag words by the
  * set-up calls) with its populations and fetches flag words only where a bulk cell has wall bits or shares the thread with a
- * non-bulk cell — 0.25 instead of 4 B/cell of flag traffic.  Never changes results.                                      */
+ * non-bulk cell — 0.25 instead of 4 B/cell of flag traffic.  Never changes results.
+ * Block kernels: fetch every flag word with the populations and ignore NLBM_FLAG_BLOCK_PLAIN (default: blocks that carry it
+ * load no flag words).                                                                                                  */
 #define NLBM_OPT_FLAG_WORDS (1 << 28)
 /* bit 29 (direct kernel): do not fetch the wall fix-up operands of the cells next to the x faces speculatively (default: they
  * travel with the streaming loads, and are used only if the cell's wall bits are exactly the x-face set).  Never changes results. */

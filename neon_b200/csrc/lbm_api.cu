@@ -643,6 +643,7 @@ static int blockStepImpl(nlbm::StepKind kind, const nlbm_block_desc* d, double o
     a.flags = d->flags;
     a.info = d->info;
     a.popPitch = (int64_t)d->n_blocks_alloc * nlbm::kBlockCells;
+    a.eagerFlags = (opts >> 28) & 1;  // NLBM_OPT_FLAG_WORDS
     a.omega = omega;
     cudaStream_t st = (cudaStream_t)stream;
     // block ranges of the view: [0, n_down) lowest layer, [n_blocks - n_up, n_blocks) highest layer

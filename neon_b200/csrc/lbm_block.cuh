@@ -38,6 +38,7 @@ struct BlockArgs
     uint32_t        firstBlock;  // the view's first block
     uint32_t        nBlocks;     // blocks of this launch
     int64_t         popPitch;    // elements between populations = n_blocks_alloc * 512
+    int32_t         eagerFlags;  // NLBM_OPT_FLAG_WORDS: fetch every flag word with the populations, ignore the block marker
     double          omega;
 };
 
@@ -211,12 +212,28 @@ __global__ void __launch_bounds__(BlockCfg<COL, T, VEC>::THREADS, BlockCfg<COL, 
 
     // the block's info line (one 128-byte line: lane i holds word i) gates every neighbour address; the CTA that ran
     // kPrefetchAhead blocks earlier pulled it into L2, and this one does the same for a later block
-    uint32_t infoWord;
+    uint32_t infoWord, word0;
     asm volatile("ld.global.nc.u32 %0, [%1];\n" : "=r"(infoWord) : "l"(a.info + (int64_t)blk * 32 + lane));
-    if (t == 0 && blockIdx.x + kPrefetchAhead < a.nBlocks)
+    // the flag word of the block's first cell carries NLBM_FLAG_BLOCK_PLAIN (set by nlbm_block_wall_mask when every cell of the
+    // block is bulk without a wall neighbour): such a block needs no flag words at all — 4 of 156 bytes per cell (ncu r02k: the
+    // flag words were three quarters of the kernel's DRAM traffic above the algorithmic bytes).  It travels next to the info
+    // line, which gates the population loads anyway, and like it was pulled into L2 by an earlier CTA.
+    asm volatile("ld.global.nc.u32 %0, [%1];\n" : "=r"(word0) : "l"(a.flags + (int64_t)blk * kBlockCells));
+    if (t == 0 && blockIdx.x + kPrefetchAhead < a.nBlocks) {
         asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.info + ((int64_t)blk + kPrefetchAhead) * 32));
-    uint32_t fl[VEC];
-    ldFlags<VEC>(a.flags + cellOff, true, fl);
+        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.flags + ((int64_t)blk + kPrefetchAhead) * kBlockCells));
+    }
+    const bool plainBlock = (word0 & NLBM_FLAG_BLOCK_PLAIN) != 0 && !a.eagerFlags;
+    uint32_t   fl[VEC];
+    ldFlags<VEC>(a.flags + cellOff, !plainBlock, fl);
+    if (plainBlock) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            fl[i] = kPlainBulk;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+        fl[i] &= ~(uint32_t)NLBM_FLAG_BLOCK_PLAIN;  // (the marker is not part of the cell's flags)
     // every population load of the thread goes out before anything is consumed
     T f[Q][VEC], edge[Q];
     blockLoadAll<L, T, VEC>(std::make_integer_sequence<int, Q>{}, popIn, a, blk, infoWord, tx, x0, y, z, f, edge);

@@ -100,7 +100,13 @@ __global__ void __launch_bounds__(512) k_block_wall_mask(const BlockGeom g, int3
                 m |= 1u << q;
         }
     }
-    g.flags[o] = (cls << NLBM_FLAG_CLASS_SHIFT) | m;
+    uint32_t w = (cls << NLBM_FLAG_CLASS_SHIFT) | m;
+    // a block whose 512 cells are all bulk without a wall neighbour is marked in the flag word of its first cell: the step kernel
+    // then skips the block's flag words (any other writer of flag words — classify, an upload — rewrites that word without the bit)
+    const int allPlain = __syncthreads_and(w == kPlainBulk);
+    if (t == 0 && allPlain)
+        w |= NLBM_FLAG_BLOCK_PLAIN;
+    g.flags[o] = w;
     if (nbad && bad)
         atomicAdd(bad, nbad);
 }

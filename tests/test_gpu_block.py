@@ -190,3 +190,42 @@ def test_partitions_on_one_gpu_match_single_partition(nb, bk, oracle, q, dtype, 
         z0, z1 = g.layers[0] * 8, min(g.layers[1] * 8, nz)
         got[:, z0:z1] = p[iters & 1].updateHostData()[:, z0:z1]
     assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))
+
+
+def test_plain_block_marker(nb, bk, oracle):
+    """NLBM_FLAG_BLOCK_PLAIN (bit 30 of the flag word of a block's first cell): nlbm_block_wall_mask sets it exactly on the
+    blocks whose 512 cells are all bulk without a wall neighbour, an upload of classes clears it, it never shows in the decoded
+    classes / masks, and the step kernel computes the same bits whether it trusts the marker (default: such blocks load no
+    flag words) or fetches every flag word (NLBM_OPT_FLAG_WORDS)."""
+    from neon_b200 import problems as P
+    from neon_b200 import _capi as capi
+    nx, ny, nz = 72, 48, 40  # 9 x 6 x 5 blocks around a sphere
+    cls = oracle.classify(1, nx, ny, nz)
+    mask = oracle.wall_mask(19, cls)
+    pop = oracle.init_pop(19, cls, np.float32)
+    omega = oracle.omega_cavity(nx)
+    grid = nb.bGrid(bk, (nx, ny, nz))
+    outs = {}
+    for opts in (0, capi.OPT_FLAG_WORDS):
+        pop0, pop1, flag = P.setup_host(grid, 19, np.float32, cls, pop)
+        raw = flag.cells[:grid.n_blocks].cpu().numpy().view(np.uint32)
+        marked = (raw[:, 0] & 0x40000000) != 0
+        assert not (raw[:, 1:] & 0x40000000).any(), "only the first cell of a block carries the marker"
+        plain = ((raw & ~np.uint32(0x40000000)) == np.uint32(capi.BULK << capi.FLAG_CLASS_SHIFT)).all(axis=1)
+        assert np.array_equal(marked, plain) and 0 < int(plain.sum()) < grid.n_blocks
+        assert np.array_equal(flag.masks(), mask) and np.array_equal(flag.classes(), cls)
+        for arith in (nb.ARITH_REFERENCE, nb.ARITH_FAST):
+            a0, a1, _ = P.setup_host(grid, 19, np.float32, cls, pop)
+            it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, a0, a1, flag, omega, arith=arith, opts=opts)
+            for _ in range(6):
+                it.run()
+            bk.syncAll()
+            outs[(opts, arith)] = it.getInput().updateHostData()
+    ref = oracle.run(19, pop, cls, mask, omega, 6)
+    for arith in (nb.ARITH_REFERENCE, nb.ARITH_FAST):
+        assert np.array_equal(outs[(0, arith)].view(np.uint8), outs[(capi.OPT_FLAG_WORDS, arith)].view(np.uint8))
+    assert np.array_equal(outs[(0, nb.ARITH_REFERENCE)].view(np.uint8), ref.view(np.uint8))
+    # an upload of classes rewrites the words: no marker until the wall mask is built again
+    flag.setClasses(cls)
+    bk.syncAll()
+    assert not (flag.cells[:grid.n_blocks].cpu().numpy().view(np.uint32) & 0x40000000).any()

@@ -317,6 +317,35 @@ class Job:
         gc.collect()
         self.torch.cuda.empty_cache()
 
+    def l2_copy(self, nbytes: int, ms_step: float):
+        """A -> B, B -> A copies of ``nbytes`` (one population field) replayed from a CUDA graph: the time a bare copy of one
+        iteration's bytes takes when everything stays in L2, and the iteration's time relative to it."""
+        torch = self.torch
+        n = nbytes // 4
+        a, b = torch.empty(n, dtype=torch.float32, device=self.bk.device), torch.ones(n, dtype=torch.float32, device=self.bk.device)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                a.copy_(b)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin()
+            for _ in range(25):
+                a.copy_(b)
+                b.copy_(a)
+            g.capture_end()
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(10):
+                g.replay()
+            e1.record(s)
+            s.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 500
+        del g, a, b
+        return {"us_per_copy": us, "GB/s": 2 * n * 4 / us / 1e3, "iteration_us": ms_step * 1e3, "iteration_over_copy": ms_step * 1e3 / us,
+                "note": "library copy kernel (torch) moving the bytes of one iteration between two L2-resident buffers, 50 per graph replay"}
+
     # ------------------------------------------------------------------------------------------ one device-resident run
     def measure(self, wl, arith_name: str, steps: int, warmup: int, sample_clocks: bool = False):
         import numpy as np
@@ -426,6 +455,12 @@ class Job:
             roofline["note"] = ("two population fields of %.1f MB fit the 126 MB L2: the HBM fraction is reported for continuity, "
                                 "it is not a bound here" % (2 * q * cells_rank * dtype.itemsize / 1e6))
             l2_note = "inputs FIT L2 (%.1f MB): not an HBM measurement" % (2 * q * cells_rank * dtype.itemsize / 1e6)
+            # the ceiling that applies instead: what a bare copy of the same bytes reaches when both buffers stay in L2 (torch's
+            # copy kernel, the one behind MEASURED_PEAKS.json's HBM number; 50 copies per CUDA-graph replay), measured here
+            try:
+                roofline["l2_resident_copy"] = self.l2_copy(q * cells_rank * dtype.itemsize, ms_step)
+            except Exception as ex:  # a ceiling that cannot be measured must not sink the line
+                roofline["l2_resident_copy"] = {"error": f"{type(ex).__name__}: {ex}"}
         res = {"workload": wl["name"], "key": wl["key"], "metric": f"LBM MLUPS (D3Q{q} {'fp32' if dtype.itemsize == 4 else 'fp64'})",
                "value": mlups, "unit": "MLUPS", "ms_per_step": ms_step, "steps": steps, "warmup": warmup, "scaling": wl["scaling"],
                "dtype": "f32" if dtype.itemsize == 4 else "f64", "arith": arith_name, "dim": list(dim), "lattice": f"D3Q{q}",

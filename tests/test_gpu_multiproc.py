@@ -94,3 +94,55 @@ def test_fused_step_and_halo_kernel_across_processes(oracle, q, dtype, world):
     ref = oracle.run(q, oracle.init_pop(q, cls, np.dtype(dtype)), cls, mask, 1.25, iters)
     assert results["timeouts"] == 0
     assert np.array_equal(results["pop"].view(np.uint8), ref.view(np.uint8))
+
+
+def _worker_full(rank, world, port, dim, iters, half, r, results, transport):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import neon_b200 as nb
+        from neon_b200 import problems as P
+        bk = nb.Backend(devices=[0] * world)
+        grid = nb.dGrid(bk, dim)
+        pop0, pop1, flag = P.setup_device(grid, 19, np.float32, P.CAVITY)
+        it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.standard, nb.TransferMode.get, pop0, pop1, flag, 1.3, arith=nb.ARITH_REFERENCE,
+                             halo_transport=transport)
+        for _ in range(iters):
+            it.run()
+        bk.syncAll()
+        # the planes of this rank inside [mid - half, mid + half), mid = the partition face between rank 0 and rank 1
+        mid = grid.z_origin + grid.nz_local if rank == 0 else grid.z_origin
+        z0, z1 = max(mid - half, grid.z_origin), min(mid + half, grid.z_origin + grid.nz_local)
+        part = None
+        if z1 > z0:
+            f = it.getInput()
+            part = (z0, f.view4[:, z0 - grid.z_origin + grid.z_halo:z1 - grid.z_origin + grid.z_halo, :r, :r].cpu().numpy())
+        results[rank] = (part, it.timeouts(), mid)
+        bk.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("transport", ["ipc", "fused"])
+def test_partition_face_of_a_full_size_box_matches_the_oracle(oracle, transport):
+    """512^3 (configs[1]'s box) as two z-slabs in two processes, OCC standard, pipelined peer-store halo (and the fused step + push
+    kernel): the cells around the partition face, next to the x = 0 / y = 0 walls, hold the bits of the CPU oracle.  By the locality
+    of the scheme a 48^3 oracle box around that place suffices: after K iterations its artificial z walls have reached K + 1 cells
+    inwards (tests/test_gpu_full_size.py does the same for the corners of single-partition boxes)."""
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device")
+    S, R, K = 48, 32, 6
+    half = S // 2 - (K + 1)  # planes on either side of the face that the artificial walls have not reached
+    dim = (512, 512, 512)
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_full, args=(2, _free_port(), dim, K, half, R, results, transport), nprocs=2, join=True)
+    mid = results[0][2]
+    assert mid == 256 and results[0][1] == 0 and results[1][1] == 0
+    got = np.concatenate([results[0][0][1], results[1][0][1]], axis=1)  # [19, 2 * half, R, R], planes mid - half .. mid + half
+    assert results[0][0][0] == mid - half and results[1][0][0] == mid and got.shape[1] == 2 * half
+    cls = oracle.classify(0, S, S, S)
+    mask = oracle.wall_mask(19, cls)
+    ref = oracle.run(19, oracle.init_pop(19, cls, np.float32), cls, mask, 1.3, K)
+    ref = ref[:, S // 2 - half:S // 2 + half, :R, :R]  # small box = [0, S) x [0, S) x [mid - S/2, mid + S/2) of the big one
+    assert np.array_equal(got.view(np.uint8), ref.view(np.uint8))

@@ -249,7 +249,9 @@ typedef struct nlbm_peer_desc {
  * behind them are scheduled when the previous launch is over and pass griddepcontrol.wait at once.  A view of more than 4096
  * planes runs as `iterations` ordinary step launches.  (A single resident grid with a grid-wide barrier between iterations was
  * built and measured in round 2 — 16.5 us per 64^3 iteration against 11.8: profiles/r02k_multi64_*, r02l_* — and retired.)
- * Same results as `iterations` step calls, bit for bit.  Capturable into a CUDA graph.                                        */
+ * Same results as `iterations` step calls, bit for bit.  Capturable into a CUDA graph.  The per-plane counters come from a pool the
+ * library keeps per device (one slice per stream that issues chains, up to 16; one per captured chain, up to 48; allocated at
+ * the first call outside a capture): a call that finds none issues `iterations` ordinary step launches instead.              */
 int nlbm_dense_step_n(int kind, const nlbm_dense_desc* d, const void* wall_cache_in, double omega, int iterations, int opts, void* stream);
 
 int nlbm_dense_step_push(int kind, const nlbm_dense_desc* d, const nlbm_peer_desc* peer, double omega, int opts, void* stream);

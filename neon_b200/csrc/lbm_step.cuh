@@ -972,20 +972,54 @@ inline cudaError_t launchStepVec(DenseArgs a, int nzView, int rowsLog2, int rpwS
     return cudaGetLastError();
 }
 
-// Plane counters of a launch chain: kChainPlanes words out of a small per-device ring (a chain owns its slice until 15 later
-// chains on the same device have been issued), allocated on first use and kept for the life of the process.
+// Plane counters of a launch chain: kChainPlanes words of a per-device pool (1 MB, allocated on first use, kept for the life of the
+// process).  Chains issued directly on a stream use that stream's own slice — chains on one stream are ordered by the stream (the
+// first launch of a chain is an ordinary one), so nothing else can touch it; up to 16 streams per device.  A chain that is being
+// captured into a CUDA graph gets a slice of its own for good (the graph may be replayed on any stream at any time); 48 of them.
+// No slice left, or the pool cannot be allocated now (first use inside a capture): nullptr — the caller issues plain launches.
 constexpr int kChainPlanes = kChainPlanesApi;
-inline unsigned* chainPlaneCounters(int dev)
+inline unsigned* chainPlaneCounters(int dev, cudaStream_t st)
 {
+    constexpr int kStreams = 16, kGraphs = 48;
+    struct Pool
+    {
+        unsigned*    base = nullptr;
+        cudaStream_t owner[kStreams] = {};
+        bool         used[kStreams] = {};
+        int          graphs = 0;
+    };
     static std::mutex mu;
-    static unsigned*  ring[64] = {};
-    static unsigned   next[64] = {};
+    static Pool       pool[64];
     if (dev < 0 || dev >= 64)
         return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (ring[dev] == nullptr && cudaMalloc(reinterpret_cast<void**>(&ring[dev]), 16 * kChainPlanes * sizeof(unsigned)) != cudaSuccess)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess)
         return nullptr;
-    return ring[dev] + (size_t)(next[dev]++ & 15u) * kChainPlanes;
+    std::lock_guard<std::mutex> lock(mu);
+    Pool&                       p = pool[dev];
+    if (p.base == nullptr) {
+        if (cap != cudaStreamCaptureStatusNone)
+            return nullptr;  // cudaMalloc would invalidate the capture
+        if (cudaMalloc(reinterpret_cast<void**>(&p.base), (size_t)(kStreams + kGraphs) * kChainPlanes * sizeof(unsigned)) != cudaSuccess) {
+            p.base = nullptr;
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+    }
+    if (cap != cudaStreamCaptureStatusNone)
+        return p.graphs < kGraphs ? p.base + (size_t)(kStreams + p.graphs++) * kChainPlanes : nullptr;
+    for (int i = 0; i < kStreams; ++i) {
+        if (p.used[i] && p.owner[i] == st)
+            return p.base + (size_t)i * kChainPlanes;
+    }
+    for (int i = 0; i < kStreams; ++i) {
+        if (!p.used[i]) {
+            p.used[i] = true;
+            p.owner[i] = st;
+            return p.base + (size_t)i * kChainPlanes;
+        }
+    }
+    return nullptr;
 }
 
 // `iterations` iterations as a chain of dependent launches (k_dense_chain); a.in / m.fieldB are the two fields
@@ -1006,22 +1040,28 @@ inline cudaError_t launchChainVec(DenseArgs a, const MultiArgs& m, int nzView, i
     if (e != cudaSuccess)
         return e;
     ChainArgs c;
-    c.planeDone = chainPlaneCounters(dev);
+    c.planeDone = chainPlaneCounters(dev, st);
     if (c.planeDone == nullptr)
-        return cudaErrorMemoryAllocation;
+        return cudaErrorNotReady;  // no counters to be had: launchMulti issues plain launches instead
     e = cudaMemsetAsync(c.planeDone, 0, grid.z * sizeof(unsigned), st);
     if (e != cudaSuccess)
         return e;
     const void *fieldA = a.in, *fieldB = m.fieldB, *keepB = a.keepCache, *keepA = m.keepCacheA;
     const unsigned tilesPerPlane = grid.x * grid.y;
     // planes whose tiles start on the counters: one chip-load of blocks (what can be resident next to the predecessor's tail)
-    int sms = 0, perSm = 0;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_dense_chain<COL, T, VEC>, kStepThreads, keepBytes);
-    if (e != cudaSuccess)
-        return e;
-    c.early = m.chainEarly != 0 ? (unsigned)m.chainEarly : ((unsigned)(sms * (perSm > 0 ? perSm : 1)) + tilesPerPlane - 1) / tilesPerPlane + 1;
+    static int slots[64] = {};  // per instantiation and device; racing host threads store the same value
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    if (slots[dev] == 0) {
+        int sms = 0, perSm = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_dense_chain<COL, T, VEC>, kStepThreads, keepBytes);
+        if (e != cudaSuccess)
+            return e;
+        slots[dev] = sms * (perSm > 0 ? perSm : 1);
+    }
+    c.early = m.chainEarly != 0 ? (unsigned)m.chainEarly : ((unsigned)slots[dev] + tilesPerPlane - 1) / tilesPerPlane + 1;
     if (c.early > grid.z)
         c.early = grid.z;
     cudaLaunchAttribute attr[1];
@@ -1079,39 +1119,54 @@ inline cudaError_t launchStep(const DenseArgs& a, int nzView, int vec, int rowsL
     return launchStepVec<COL, T, 1>(a, nzView, rowsLog2, rpwSel, st);
 }
 
-// nlbm_dense_step_n: the launch chain; a view with more planes than the chain has counters runs as plain step launches
+// `iterations` ordinary step launches, the two fields swapping roles
+template <class COL, typename T>
+inline cudaError_t launchPlainSteps(const DenseArgs& a, const MultiArgs& m, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
+{
+    DenseArgs   b = a;
+    const void *fieldA = a.in, *keepB = a.keepCache;
+    for (int it = 0; it < m.iterations; ++it) {
+        const bool even = (it & 1) == 0;
+        b.in = even ? fieldA : m.fieldB;
+        b.out = const_cast<void*>(even ? m.fieldB : fieldA);
+        b.keepCache = even ? keepB : m.keepCacheA;
+        cudaError_t e = launchStep<COL, T>(b, nzView, vec, rowsLog2, rpwSel, st);
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
+
+// nlbm_dense_step_n: the launch chain; a view with more planes than a chain has counters, or a call that finds no counters free,
+// runs as plain step launches
 template <class COL, typename T>
 inline cudaError_t launchMulti(const DenseArgs& a, const MultiArgs& m, int nzView, int vec, int rowsLog2, int rpwSel, cudaStream_t st)
 {
-    if (nzView > kChainPlanes) {
-        DenseArgs   b = a;
-        const void *fieldA = a.in, *keepB = a.keepCache;
-        for (int it = 0; it < m.iterations; ++it) {
-            const bool even = (it & 1) == 0;
-            b.in = even ? fieldA : m.fieldB;
-            b.out = const_cast<void*>(even ? m.fieldB : fieldA);
-            b.keepCache = even ? keepB : m.keepCacheA;
-            cudaError_t e = launchStep<COL, T>(b, nzView, vec, rowsLog2, rpwSel, st);
-            if (e != cudaSuccess)
-                return e;
-        }
-        return cudaSuccess;
-    }
+    if (nzView > kChainPlanes)
+        return launchPlainSteps<COL, T>(a, m, nzView, vec, rowsLog2, rpwSel, st);
     constexpr int maxVec = 16 / (int)sizeof(T);
-    if (vec <= 0 || vec > maxVec) {
-        vec = maxVec;
-        while (vec > 1 && COL::Q * vec * (int)sizeof(T) / 4 > 80)
-            vec >>= 1;
+    int           cv = vec;
+    if (cv <= 0 || cv > maxVec) {
+        cv = maxVec;
+        while (cv > 1 && COL::Q * cv * (int)sizeof(T) / 4 > 80)
+            cv >>= 1;
     }
-    while (vec > 1 && (a.pitch_y % (32 * vec) != 0))
-        vec >>= 1;
-    if constexpr (maxVec >= 4) {
-        if (vec == 4)
-            return launchChainVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
+    while (cv > 1 && (a.pitch_y % (32 * cv) != 0))
+        cv >>= 1;
+    cudaError_t e;
+    if (maxVec >= 4 && cv == 4) {
+        if constexpr (maxVec >= 4)
+            e = launchChainVec<COL, T, 4>(a, m, nzView, rowsLog2, rpwSel, st);
+        else
+            e = cudaErrorInvalidValue;
+    } else if (cv >= 2) {
+        e = launchChainVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
+    } else {
+        e = launchChainVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
     }
-    if (vec >= 2)
-        return launchChainVec<COL, T, 2>(a, m, nzView, rowsLog2, rpwSel, st);
-    return launchChainVec<COL, T, 1>(a, m, nzView, rowsLog2, rpwSel, st);
+    if (e == cudaErrorNotReady)
+        return launchPlainSteps<COL, T>(a, m, nzView, vec, rowsLog2, rpwSel, st);
+    return e;
 }
 
 }  // namespace nlbm

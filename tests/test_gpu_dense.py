@@ -249,6 +249,27 @@ def test_several_iterations_in_one_launch(nb, bk, oracle, q, store, dim, geom, i
     assert np.array_equal(it.getInput().updateHostData().view(np.uint8), ref3.view(np.uint8))
 
 
+def test_launch_chain_runs_out_of_counters_gracefully(nb, bk, oracle):
+    """The launch chain takes its per-plane counters from a small pool (one slice per captured chain, 48 per device): the 49th
+    and later captures find none and are recorded as ordinary step launches — same bits."""
+    from neon_b200 import problems as P
+    dim, q, iters = (40, 24, 20), 19, 4
+    cls = oracle.classify(1, *dim)
+    mask = oracle.wall_mask(q, cls)
+    pop = oracle.init_pop(q, cls, np.float32)
+    omega = oracle.omega_cavity(max(dim))
+    grid = nb.dGrid(bk, dim)
+    pop0, pop1, flag = P.setup_host(grid, q, np.float32, cls, pop)
+    it = nb.LbmIteration(nb.StencilSemantic.streaming, nb.Occ.none, nb.TransferMode.get, pop0, pop1, flag, omega, arith=nb.ARITH_REFERENCE)
+    done = 0
+    for k in range(56):
+        it.__dict__.pop("_graphs", None)  # a fresh capture every time (the graphs, and their slices, stay alive in `keep`)
+        done += it.runGraph(iters, many=True)
+    bk.syncAll()
+    ref = oracle.run(q, pop, cls, mask, omega, done)
+    assert np.array_equal(it.getInput().updateHostData().view(np.uint8), ref.view(np.uint8))
+
+
 def test_device_setup_matches_oracle(nb, bk, oracle):
     """nlbm_dense_classify / wall_mask / init_pop against the oracle, bit for bit, all geometries."""
     from neon_b200 import problems as P

@@ -1,5 +1,5 @@
 #!/bin/bash
-# final kernels of round 1: full GPU suite, bench line, launch list, ncu --set full captures, bench matrix
+# one-GPU pass: full GPU suite, bench line, launch list, ncu --set full captures, bench matrix
 mkdir -p gpurun_out
 O=gpurun_out
 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 > $O/pytest_gpu_final.log
@@ -17,6 +17,6 @@ for w in sphere bcavity512 d3q27f64 cavity64 cavity128 cavity256 slab1024 cavity
   timeout 300 python bench.py --workload $w --steps 50 --warmup 5 --no-cpu --no-e2e >> $O/bench_matrix_final.log 2>> $O/bench_matrix_final.err
 done
 timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu --no-e2e --arith reference >> $O/bench_matrix_final.log 2>> $O/bench_matrix_final.err
-for e in 1 2 3; do
+for e in 3; do
   timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu --no-e2e --experiment $e >> $O/bench_matrix_final.log 2>> $O/bench_matrix_final.err
 done

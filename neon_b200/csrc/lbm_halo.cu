@@ -49,13 +49,29 @@ struct Push2Args
     uint32_t* counter;
     uint32_t  value, blocks;
 };
-__global__ void __launch_bounds__(256) k_face_push2(const char* __restrict__ src, const Push2Args a, const size_t vecPerPlane)
+// Few, fat blocks on purpose (1024 threads, four 16-byte copies in flight per thread, at most kPushBlocksPerPlane blocks per plane):
+// the kernel runs at high priority NEXT TO the INTERNAL step kernel, whose blocks own half an SM's registers each — every
+// resident block of this kernel, however small, keeps one of them off the chip for as long as it lives.  A thousand short blocks
+// of 256 threads (round 2, first half) cost the INTERNAL kernel ~45 us per iteration; the stores are bound by NVLink latency, not
+// by how many SMs issue them, and the faces have a whole iteration to arrive.
+constexpr int kPushThreads = 1024, kPushUnroll = 4, kPushBlocksPerPlane = 4;
+__global__ void __launch_bounds__(kPushThreads) k_face_push2(const char* __restrict__ src, const Push2Args a, const size_t vecPerPlane)
 {
     const int    p = blockIdx.y;
     const uint4* s = reinterpret_cast<const uint4*>(src + a.pl.src[p]);
     uint4*       d = reinterpret_cast<uint4*>(a.dst[p < a.nUp ? 0 : 1] + a.pl.dst[p]);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecPerPlane; i += stride)
+    size_t       i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kPushUnroll - 1) * stride < vecPerPlane; i += kPushUnroll * stride) {
+        uint4 v[kPushUnroll];
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k)
+            v[k] = __ldcs(s + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k)
+            d[i + k * stride] = v[k];
+    }
+    for (; i < vecPerPlane; i += stride)
         d[i] = __ldcs(s + i);
     __threadfence_system();  // my peer stores are visible system-wide before my block counts as done
     __syncthreads();
@@ -78,9 +94,9 @@ cudaError_t launchFacePush2(const void* src, const PlaneList& pl, int nUp, void*
     if (pl.n == 0 || planeBytes == 0)
         return cudaSuccess;
     const size_t vecs = planeBytes / 16;
-    size_t       bx = (vecs + 256 * 4 - 1) / (256 * 4);
-    if (bx > 148 * 2)
-        bx = 148 * 2;
+    size_t       bx = (vecs + kPushThreads * kPushUnroll - 1) / (kPushThreads * kPushUnroll);
+    if (bx > (size_t)kPushBlocksPerPlane)
+        bx = kPushBlocksPerPlane;
     if (bx == 0)
         bx = 1;
     Push2Args a;
@@ -94,7 +110,7 @@ cudaError_t launchFacePush2(const void* src, const PlaneList& pl, int nUp, void*
     a.value = value;
     a.blocks = (uint32_t)(bx * pl.n);
     dim3 grid((unsigned)bx, pl.n);
-    k_face_push2<<<grid, 256, 0, st>>>((const char*)src, a, vecs);
+    k_face_push2<<<grid, kPushThreads, 0, st>>>((const char*)src, a, vecs);
     return cudaGetLastError();
 }
 

@@ -125,15 +125,33 @@ struct SliceArgs
     int      sliceOff, vecPerSlice;     // byte offset of the slice inside a block tile, 16-byte vectors per slice
     int      blockBytes;
 };
-__global__ void __launch_bounds__(256) k_block_slice_copy(const char* __restrict__ src, char* __restrict__ dst, const SliceArgs s)
+// (few fat blocks, several copies in flight per thread: see k_face_push2)
+__global__ void __launch_bounds__(kPushThreads) k_block_slice_copy(const char* __restrict__ src, char* __restrict__ dst, const SliceArgs s)
 {
     const int64_t total = (int64_t)s.nBlocks * s.vecPerSlice;
     const int     c = blockIdx.y;
     const char*   sp = src + s.comps[c] * s.srcPopPitch + (int64_t)s.srcFirst * s.blockBytes + s.sliceOff;
     char*         dp = dst + s.comps[c] * s.dstPopPitch + (int64_t)s.dstFirst * s.blockBytes + s.sliceOff;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    auto          offsetOf = [&](int64_t i) {
         const int64_t b = i / s.vecPerSlice, v = i - b * s.vecPerSlice;
-        const int64_t o = b * s.blockBytes + v * 16;
+        return b * s.blockBytes + v * 16;
+    };
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kPushUnroll - 1) * stride < total; i += kPushUnroll * stride) {
+        uint4   v[kPushUnroll];
+        int64_t o[kPushUnroll];
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k) {
+            o[k] = offsetOf(i + k * stride);
+            v[k] = __ldcs(reinterpret_cast<const uint4*>(sp + o[k]));
+        }
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k)
+            *reinterpret_cast<uint4*>(dp + o[k]) = v[k];
+    }
+    for (; i < total; i += stride) {
+        const int64_t o = offsetOf(i);
         *reinterpret_cast<uint4*>(dp + o) = __ldcs(reinterpret_cast<const uint4*>(sp + o));
     }
 }
@@ -156,11 +174,13 @@ cudaError_t launchBlockSliceCopy(const void* src, void* dst, int elemBytes, cons
     s.sliceOff = zSlice * 64 * elemBytes;
     s.vecPerSlice = 64 * elemBytes / 16;
     const int64_t total = (int64_t)nBlocks * s.vecPerSlice;
-    int64_t       bx = (total + 255) / 256;
-    if (bx > 148 * 4)
-        bx = 148 * 4;
+    int64_t       bx = (total + kPushThreads * kPushUnroll - 1) / (kPushThreads * kPushUnroll);
+    if (bx > kPushBlocksPerPlane)
+        bx = kPushBlocksPerPlane;
+    if (bx < 1)
+        bx = 1;
     dim3 grid((unsigned)bx, ncomps);
-    k_block_slice_copy<<<grid, 256, 0, st>>>((const char*)src, (char*)dst, s);
+    k_block_slice_copy<<<grid, kPushThreads, 0, st>>>((const char*)src, (char*)dst, s);
     return cudaGetLastError();
 }
 

@@ -11,14 +11,31 @@
 
 namespace nlbm {
 
-__global__ void __launch_bounds__(256) k_plane_copy(const char* __restrict__ src, char* __restrict__ dst, const PlaneList pl,
-                                                    const size_t vecPerPlane)
+// Copy kernels of the halo update: few, fat blocks on purpose (1024 threads, four 16-byte copies in flight per thread, a handful of
+// blocks per plane).  They run at high priority NEXT TO the INTERNAL step kernel, whose blocks own half an SM's registers each —
+// every resident block of a copy kernel, however small, keeps one of them off the chip for as long as it lives.  A few thousand
+// short blocks of 256 threads (round 2, first half) cost the INTERNAL kernel ~25-45 us per iteration; the stores are bound by the
+// NVLink round trip, not by how many SMs issue them, and the faces have a whole iteration to arrive.
+constexpr int kPushThreads = 1024, kPushUnroll = 4, kPushBlocksPerPlane = 4, kCopyBlocksPerPlane = 8;
+
+__global__ void __launch_bounds__(kPushThreads) k_plane_copy(const char* __restrict__ src, char* __restrict__ dst, const PlaneList pl,
+                                                             const size_t vecPerPlane)
 {
     const int    p = blockIdx.y;
     const uint4* s = reinterpret_cast<const uint4*>(src + pl.src[p]);
     uint4*       d = reinterpret_cast<uint4*>(dst + pl.dst[p]);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < vecPerPlane; i += stride)
+    size_t       i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kPushUnroll - 1) * stride < vecPerPlane; i += kPushUnroll * stride) {
+        uint4 v[kPushUnroll];
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k)
+            v[k] = __ldcs(s + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < kPushUnroll; ++k)
+            d[i + k * stride] = v[k];
+    }
+    for (; i < vecPerPlane; i += stride)
         d[i] = __ldcs(s + i);
 }
 
@@ -27,13 +44,13 @@ cudaError_t launchPlaneCopy(const void* src, void* dst, const PlaneList& pl, siz
     if (pl.n == 0 || planeBytes == 0)
         return cudaSuccess;
     const size_t vecs = planeBytes / 16;
-    size_t       bx = (vecs + 256 * 4 - 1) / (256 * 4);
-    if (bx > 148 * 4)
-        bx = 148 * 4;
+    size_t       bx = (vecs + kPushThreads * kPushUnroll - 1) / (kPushThreads * kPushUnroll);
+    if (bx > (size_t)kCopyBlocksPerPlane)
+        bx = kCopyBlocksPerPlane;
     if (bx == 0)
         bx = 1;
     dim3 grid((unsigned)bx, pl.n);
-    k_plane_copy<<<grid, 256, 0, st>>>((const char*)src, (char*)dst, pl, vecs);
+    k_plane_copy<<<grid, kPushThreads, 0, st>>>((const char*)src, (char*)dst, pl, vecs);
     return cudaGetLastError();
 }
 
@@ -49,12 +66,7 @@ struct Push2Args
     uint32_t* counter;
     uint32_t  value, blocks;
 };
-// Few, fat blocks on purpose (1024 threads, four 16-byte copies in flight per thread, at most kPushBlocksPerPlane blocks per plane):
-// the kernel runs at high priority NEXT TO the INTERNAL step kernel, whose blocks own half an SM's registers each — every
-// resident block of this kernel, however small, keeps one of them off the chip for as long as it lives.  A thousand short blocks
-// of 256 threads (round 2, first half) cost the INTERNAL kernel ~45 us per iteration; the stores are bound by NVLink latency, not
-// by how many SMs issue them, and the faces have a whole iteration to arrive.
-constexpr int kPushThreads = 1024, kPushUnroll = 4, kPushBlocksPerPlane = 4;
+// (few fat blocks: see k_plane_copy)
 __global__ void __launch_bounds__(kPushThreads) k_face_push2(const char* __restrict__ src, const Push2Args a, const size_t vecPerPlane)
 {
     const int    p = blockIdx.y;

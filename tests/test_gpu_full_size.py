@@ -4,6 +4,8 @@ R + K of that corner.  The same corner of a SMALL box — which the CPU oracle i
 bits (REFERENCE arithmetic) as the corner of the 512^3 ... 1024 x 1024 x 512 box on the GPU, as long as R + K stays clear of the
 small box's far walls.  Both the corner at the origin and the one at (nx-1, ny-1, nz-1) — the lid, the outlet, and element offsets
 beyond 2^31 and 2^33 — are compared, on dGrid and on bGrid."""
+import gc
+
 import numpy as np
 import pytest
 
@@ -58,6 +60,7 @@ def test_corners_of_full_size_boxes_match_the_oracle(nb, bk, oracle, q, dtype, d
     assert R <= S - 1 - K and R % 8 == 0
     nx, ny, nz = dim
     omega = 1.3
+    gc.collect()  # fields of earlier tests that only a reference cycle keeps alive
     torch.cuda.empty_cache()
     need = 2 * q * nx * ny * nz * np.dtype(dtype).itemsize + 5 * nx * ny * nz + (2 << 30)
     if torch.cuda.mem_get_info()[0] < need:
